@@ -1,0 +1,376 @@
+// igemm.cu -- K6: int8 GEMM C[i,j] = sum_k A[i,k] * B[j,k] with exact int32 accumulators on the
+// sm_100a tensor pipe (tcgen05.mma kind::i8, accumulators in TMEM), optional fused mm_dequant epilogue.
+//
+// Replaces igemmlt<FORMATB,32,0> (reference op_gemm.cpp:541-603 -> vendored blas_utils.h:459-724 ->
+// oneDNN s8*s8->s32; originally cublasLtMatmul on Turing/Ampere IMMA layouts) and, when the epilogue
+// is fused, kdequant_mm_int32_fp16 (kernel_quant.cpp:3848-3987).
+//
+// Design (DESIGN.md "K6"): persistent warp-specialised CTA per SM --
+//   warp 0   : TMA producer, 128x128 B (A) + 256x128 B (B) K-major tiles, SWIZZLE_128B, 4-stage mbarrier ring
+//   warp 1   : TMEM owner + single-thread tcgen05.mma issuer (M=128, N=256, K=32 per instruction),
+//              two 256-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warps 2-5: epilogue, tcgen05.ld 32x32b -> registers -> (int32 | dequant -> fp16) -> global
+// Operands are ROW-MAJOR int8 (K contiguous) -- the layout TMA + UMMA consume directly.  The
+// reference's col32 / col_turing / col_ampere operands (Turing/Ampere IMMA layouts) are accepted by the
+// cigemmlt_* ABI wrappers, which re-layout through scratch (correct, slower; the B200-native entry
+// points are cigemm_rowmajor_*).
+#include <cudaTypedefs.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace bnb {
+
+// implemented in int8_quant.cu
+void untransform_s8(int fmt, const signed char *A, signed char *out, int rows, int cols);
+template <typename E> void to_col32(const E *A, E *out, int rows, int cols);
+
+// ------------------------------------------------------------------------------------------------
+// tensor map helper
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+bool make_tmap_2d(CUtensorMap *map, const void *base, int elem_bytes, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                  uint32_t box_cols, bool is_16bit_float, bool is_bf16) {
+  auto fn = get_encode_fn();
+  if (!fn) { latch_error(cudaErrorNotSupported, "cuTensorMapEncodeTiled unavailable"); return false; }
+  CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  if (is_16bit_float) dt = is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  else if (elem_bytes == 4) dt = CU_TENSOR_MAP_DATA_TYPE_INT32;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { latch_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled failed"); return false; }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int BM = 128, BN = 256, BK = 128;  // BK in bytes == int8 elements
+constexpr int kStages = 4;
+constexpr int kStageA = BM * BK, kStageB = BN * BK, kStageBytes = kStageA + kStageB;  // 16 KB + 32 KB
+constexpr int kIgemmThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr int kIgemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * (4 + 2) /*col stats + bias*/;
+
+enum { EPI_INT32 = 0, EPI_DEQUANT_FP16 = 1 };
+
+struct IgemmArgs {
+  int M, N, K;
+  int *C;                  // EPI_INT32: row-major [M,N]
+  const float *rowStats;   // EPI_DEQUANT_FP16
+  const float *colStats;
+  const __half *bias;      // may be null
+  __half *out;             // row-major [M,N]
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(kIgemmThreads, 1)
+k_igemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
+  uint64_t *full = bars, *empty = bars + kStages, *tfull = bars + 2 * kStages, *tempty = bars + 2 * kStages + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+  float *s_cs = reinterpret_cast<float *>(smem + kStages * kStageBytes + 256);  // [2][BN]
+  __half *s_bias = reinterpret_cast<__half *>(s_cs + 2 * BN);                   // [2][BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (a.M + BM - 1) / BM, num_n = (a.N + BN - 1) / BN;
+  const int tiles = num_m * num_n, kblocks = (a.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmA); tc::prefetch_tmap(&tmB); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; s++) { tc::mbar_init(tc::smem_u32(full + s), 1); tc::mbar_init(tc::smem_u32(empty + s), 1); }
+      for (int i = 0; i < 2; i++) { tc::mbar_init(tc::smem_u32(tfull + i), 1); tc::mbar_init(tc::smem_u32(tempty + i), 4); }
+      tc::fence_barrier_init();
+    }
+    __syncwarp();
+    tc::tmem_alloc(tc::smem_u32(tmem_slot), kTmemCols);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        for (int kb = 0; kb < kblocks; kb++) {
+          tc::mbar_wait(tc::smem_u32(empty + stage), phase ^ 1);
+          const uint32_t fb = tc::smem_u32(full + stage);
+          tc::mbar_arrive_expect_tx(fb, kStageBytes);
+          uint8_t *sa = smem + stage * kStageBytes;
+          tc::tma_load_2d(tc::smem_u32(sa), &tmA, fb, kb * BK, m_blk * BM);
+          tc::tma_load_2d(tc::smem_u32(sa + kStageA), &tmB, fb, kb * BK, n_blk * BN);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::umma_idesc(tc::kCFormatS32, 1u, BM, BN);
+      int stage = 0; uint32_t phase = 0; int it = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
+        const int acc = it & 1; const uint32_t use = (uint32_t)(it >> 1);
+        tc::mbar_wait(tc::smem_u32(tempty + acc), (use & 1) ^ 1);
+        tc::fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; kb++) {
+          tc::mbar_wait(tc::smem_u32(full + stage), phase);
+          tc::fence_after_sync();
+          const uint32_t sa = tc::smem_u32(smem + stage * kStageBytes);
+          const uint64_t adesc = tc::umma_desc_sw128_kmajor(sa);
+          const uint64_t bdesc = tc::umma_desc_sw128_kmajor(sa + kStageA);
+#pragma unroll
+          for (int k = 0; k < BK / 32; k++)
+            tc::umma_i8(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          tc::umma_commit(tc::smem_u32(empty + stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        tc::umma_commit(tc::smem_u32(tfull + acc));
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =================
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;  // 0..127
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
+      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      const int acc = it & 1; const uint32_t use = (uint32_t)(it >> 1);
+      const int row = m_blk * BM + q * 32 + lane;
+      float rs = 0.f;
+      if (EPI == EPI_DEQUANT_FP16) {
+        // stage this tile's column stats / bias; the buffer `acc` was last read two tiles ago
+        for (int j = et; j < BN; j += 128) {
+          const int col = n_blk * BN + j;
+          s_cs[acc * BN + j] = col < a.N ? a.colStats[col] : 0.f;
+          s_bias[acc * BN + j] = (a.bias != nullptr && col < a.N) ? a.bias[col] : __float2half(0.f);
+        }
+        rs = row < a.M ? a.rowStats[row] : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      tc::mbar_wait(tc::smem_u32(tfull + acc), use & 1);
+      tc::fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; c++) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32b_x32(taddr + c * 32, v);
+        tc::tmem_ld_wait();
+        const int col0 = n_blk * BN + c * 32;
+        if (row < a.M && col0 < a.N) {
+          if (EPI == EPI_INT32) {
+            int *dst = a.C + (long)row * a.N + col0;
+            if (col0 + 32 <= a.N && (a.N & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; j++)
+                reinterpret_cast<int4 *>(dst)[j] = make_int4((int)v[4 * j], (int)v[4 * j + 1], (int)v[4 * j + 2], (int)v[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (col0 + j < a.N) dst[j] = (int)v[j];
+            }
+          } else {
+            __half h[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              float t = __fmul_rn(__int2float_rn((int)v[j]), 6.200012e-05f);
+              t = __fmul_rn(t, rs);
+              t = __fmul_rn(t, s_cs[acc * BN + c * 32 + j]);
+              t = __fadd_rn(t, __half2float(s_bias[acc * BN + c * 32 + j]));
+              h[j] = __float2half_rn(t);
+            }
+            __half *dst = a.out + (long)row * a.N + col0;
+            if (col0 + 32 <= a.N && (a.N & 7) == 0) {
+#pragma unroll
+              for (int j = 0; j < 4; j++) reinterpret_cast<uint4 *>(dst)[j] = reinterpret_cast<const uint4 *>(h)[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (col0 + j < a.N) dst[j] = h[j];
+            }
+          }
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(tempty + acc));
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT path (dp4a) for shapes TMA cannot describe (K % 16 != 0 or unaligned bases).  Exact as well.
+// ------------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(256) k_igemm_simt(const signed char *__restrict__ A, const signed char *__restrict__ B,
+                                                    const IgemmArgs a) {
+  __shared__ signed char sA[64][68], sB[64][68];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  int acc[4][4] = {};
+  for (int k0 = 0; k0 < a.K; k0 += 64) {
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+      const int r = i / 64, c = i % 64;
+      sA[r][c] = (m0 + r < a.M && k0 + c < a.K) ? A[(long)(m0 + r) * a.K + k0 + c] : 0;
+      sB[r][c] = (n0 + r < a.N && k0 + c < a.K) ? B[(long)(n0 + r) * a.K + k0 + c] : 0;
+    }
+    __syncthreads();
+    for (int kk = 0; kk < 64; kk += 4) {
+      int av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        av[i] = *reinterpret_cast<const int *>(&sA[ty * 4 + i][kk]);
+        bv[i] = *reinterpret_cast<const int *>(&sB[tx * 4 + i][kk]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = __dp4a(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = m0 + ty * 4 + i, c = n0 + tx * 4 + j;
+      if (r < a.M && c < a.N) {
+        if (EPI == EPI_INT32) a.C[(long)r * a.N + c] = acc[i][j];
+        else {
+          float t = __fmul_rn(__int2float_rn(acc[i][j]), 6.200012e-05f);
+          t = __fmul_rn(t, a.rowStats[r]);
+          t = __fmul_rn(t, a.colStats[c]);
+          t = __fadd_rn(t, a.bias ? __half2float(a.bias[c]) : 0.f);
+          a.out[(long)r * a.N + c] = __float2half_rn(t);
+        }
+      }
+    }
+}
+
+static int env_force_simt() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("BNB_B200_IGEMM_IMPL"); v = (e && e[0] == 's') ? 1 : 0; }
+  return v;
+}
+
+template <int EPI>
+static int igemm_rowmajor(const signed char *A, const signed char *B, const IgemmArgs &a) {
+  if (a.M <= 0 || a.N <= 0) return 0;
+  if (a.K <= 0) { latch_error(cudaErrorInvalidValue, "igemm: k must be > 0"); return 2; }
+  cudaStream_t st = current_stream();
+  const bool tma_ok = (a.K % 16 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0) &&
+                      (reinterpret_cast<uintptr_t>(B) % 16 == 0) && !env_force_simt();
+  if (tma_ok) {
+    CUtensorMap tmA, tmB;
+    if (!make_tmap_2d(&tmA, A, 1, (uint64_t)a.M, (uint64_t)a.K, BM, BK, false, false)) return 2;
+    if (!make_tmap_2d(&tmB, B, 1, (uint64_t)a.N, (uint64_t)a.K, BN, BK, false, false)) return 2;
+    static bool attr_set = false;
+    if (!attr_set) {
+      latch_error(cudaFuncSetAttribute(k_igemm_tcgen05<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIgemmSmem), "igemm smem attr");
+      attr_set = true;
+    }
+    const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
+    int sms = kNumSMs, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = tiles < sms ? tiles : sms;
+    k_igemm_tcgen05<EPI><<<grid, kIgemmThreads, kIgemmSmem, st>>>(tmA, tmB, a);
+  } else {
+    dim3 grid(ceil_div(a.N, 64), ceil_div(a.M, 64));
+    k_igemm_simt<EPI><<<grid, 256, 0, st>>>(A, B, a);
+  }
+  cudaError_t e = cudaGetLastError();
+  latch_error(e, "igemm launch");
+  return e == cudaSuccess ? 0 : 2;
+}
+
+int igemm_rowmajor_32(int m, int n, int k, const signed char *A, const signed char *B, int *C) {
+  IgemmArgs a{};
+  a.M = m; a.N = n; a.K = k; a.C = C;
+  return igemm_rowmajor<EPI_INT32>(A, B, a);
+}
+int igemm_rowmajor_dequant_fp16(int m, int n, int k, const signed char *A, const signed char *B, const float *rowStats,
+                                const float *colStats, const __half *bias, __half *out) {
+  IgemmArgs a{};
+  a.M = m; a.N = n; a.K = k; a.rowStats = rowStats; a.colStats = colStats; a.bias = bias; a.out = out;
+  return igemm_rowmajor<EPI_DEQUANT_FP16>(A, B, a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// reference ABI: A col32, B col_turing / col_ampere, C col32 (int32, or saturated int8 with fp32 alpha)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_scale_to_s8(const int *__restrict__ C, signed char *__restrict__ out, const float *__restrict__ row_scale,
+                              int m, int n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)m * n) return;
+  const float alpha = row_scale ? row_scale[i / n] : 1.0f;
+  const int q = __float2int_rn(__fmul_rn(__int2float_rn(C[i]), alpha));
+  out[i] = (signed char)max(-128, min(127, q));
+}
+
+int igemmlt(int fmtB, int dtype_out, bool scale_rows, int m, int n, int k, const signed char *A, const signed char *B,
+            void *C, const float *row_scale, int lda, int ldb, int ldc) {
+  if (m <= 0 || n <= 0) return 0;
+  if (k <= 0 || lda != m * 32 || ldc != m * 32) { latch_error(cudaErrorInvalidValue, "igemmlt: lda/ldc must be m*32 (col32)"); return 2; }
+  (void)ldb;
+  if (scale_rows && row_scale == nullptr) return 2;
+  cudaStream_t st = current_stream();
+  signed char *Arm = nullptr, *Brm = nullptr, *C8 = nullptr;
+  int *Crm = nullptr;
+  const size_t szA = (size_t)m * k, szB = (size_t)n * k, szC = (size_t)m * n * sizeof(int);
+  if (cudaMallocAsync(&Arm, szA, st) != cudaSuccess || cudaMallocAsync(&Brm, szB, st) != cudaSuccess ||
+      cudaMallocAsync(&Crm, szC, st) != cudaSuccess) {
+    latch_error(cudaGetLastError(), "igemmlt scratch");
+    return 2;
+  }
+  untransform_s8(COL32, A, Arm, m, k);
+  untransform_s8(fmtB, B, Brm, n, k);
+  int rc = igemm_rowmajor_32(m, n, k, Arm, Brm, Crm);
+  if (rc == 0) {
+    if (dtype_out == 32) {
+      to_col32<int>(Crm, reinterpret_cast<int *>(C), m, n);
+    } else {
+      if (cudaMallocAsync(&C8, (size_t)m * n, st) != cudaSuccess) rc = 2;
+      else {
+        k_scale_to_s8<<<(unsigned)ceil_div_ll((long)m * n, 256), 256, 0, st>>>(Crm, C8, scale_rows ? row_scale : nullptr, m, n);
+        to_col32<signed char>(C8, reinterpret_cast<signed char *>(C), m, n);
+        cudaFreeAsync(C8, st);
+      }
+    }
+  }
+  cudaFreeAsync(Arm, st);
+  cudaFreeAsync(Brm, st);
+  cudaFreeAsync(Crm, st);
+  return rc;
+}
+
+}  // namespace bnb

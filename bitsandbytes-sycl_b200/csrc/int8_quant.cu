@@ -1,0 +1,399 @@
+// int8_quant.cu -- K5/K7 and the layout helpers of the LLM.int8 path for sm_100a:
+//   get_col_row_stats   (reference kgetColRowStats,      kernel_quant.cpp:3214-3379)
+//   double_rowcol_quant (reference kDoubleRowColQuant,   kernel_quant.cpp:3384-3512)
+//   transform_row2fmt   (reference kTransformRowToFormat,kernel_quant.cpp:3516-3841)
+//   dequant_mm_int32    (reference kdequant_mm_int32_fp16,kernel_quant.cpp:3848-3987)
+//   extract_outliers    (reference kExtractOutliers,     kernel_quant.cpp:3992-4053)
+// All are HBM streams.  Work decomposition: one WARP owns a (band of rows) x (256-column segment),
+// i.e. the reference's 16x256 nnz tiles stacked; every lane moves 16 bytes per access, the column
+// statistics live in registers across the band, row statistics are warp-shuffle reductions, and the
+// float max is merged with integer atomicMax (all values are >= 0, so the int order is the float order).
+#include "common.cuh"
+
+namespace bnb {
+
+constexpr int kBandRows = 32;   // rows per warp band (2 of the reference's 16-row nnz tiles)
+constexpr float kMMDequantConst = 6.200012e-05f;  // kernel_quant.cpp:3846
+
+__device__ __forceinline__ void atomic_max_nonneg(float *addr, float v) {
+  // v >= +0; existing value may be negative (caller initialises to -50000, functional.py:2413-2415)
+  if (*addr < v) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5a: row/col absmax (+ per (tile,row) outlier counts when thr > 0)
+// ------------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_col_row_stats(const __half *__restrict__ A, float *rowStats, float *colStats,
+                                                       int *nnz_count_row, float thr, int rows, int cols,
+                                                       int col_tiles, int nbands) {
+  const int lane = threadIdx.x & 31;
+  const long wid = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (wid >= (long)nbands * col_tiles) return;
+  const int band = (int)(wid / col_tiles), ct = (int)(wid % col_tiles);
+  const int c0 = ct * 256 + lane * 8;
+  const int r0 = band * kBandRows;
+  const bool sparse = thr > 0.0f;
+
+  float cmax[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) cmax[j] = 0.0f;  // |x| >= 0, and padded / outlier entries count as 0
+
+  for (int rb = 0; rb < kBandRows; rb += 8) {
+    uint4 raw[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int r = r0 + rb + u;
+      raw[u] = make_uint4(0, 0, 0, 0);
+      if (r < rows) {
+        if (VEC) {
+          if (c0 < cols) raw[u] = ld_stream_u4(A + (long)r * cols + c0);
+        } else {
+          __half *p = reinterpret_cast<__half *>(&raw[u]);
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            if (c0 + j < cols) p[j] = A[(long)r * cols + c0 + j];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int r = r0 + rb + u;
+      const __half *p = reinterpret_cast<const __half *>(&raw[u]);
+      float rmax = 0.0f;
+      int cnt = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        float v = fabsf(__half2float(p[j]));
+        if (sparse && v >= thr) { cnt++; v = 0.0f; }
+        cmax[j] = fmaxf(cmax[j], v);
+        rmax = fmaxf(rmax, v);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+      if (sparse) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      }
+      if (lane == 0) {
+        if (r < rows) atomic_max_nonneg(rowStats + r, rmax);
+        // tile id = (r/16)*col_tiles + ct; slot +1 (slot 0 stays 0 for the caller's cumsum)
+        if (sparse && nnz_count_row && r < ((rows + 15) / 16) * 16)
+          nnz_count_row[((long)(r / 16) * col_tiles + ct) * 16 + (r % 16) + 1] = (r < rows) ? cnt : 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+    if (c0 + j < cols) atomic_max_nonneg(colStats + c0 + j, cmax[j]);
+}
+
+void get_col_row_stats(const __half *A, float *rowStats, float *colStats, int *nnz_count_row, float thr, int rows,
+                       int cols) {
+  if (rows <= 0 || cols <= 0) return;
+  const int col_tiles = ceil_div(cols, 256);
+  const int nbands = ceil_div(rows, kBandRows);
+  const long nwarps = (long)nbands * col_tiles;
+  const unsigned grid = (unsigned)ceil_div_ll(nwarps, 8);
+  const bool vec = (cols % 8 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0);
+  if (vec) k_col_row_stats<true><<<grid, 256, 0, current_stream()>>>(A, rowStats, colStats, nnz_count_row, thr, rows, cols, col_tiles, nbands);
+  else k_col_row_stats<false><<<grid, 256, 0, current_stream()>>>(A, rowStats, colStats, nnz_count_row, thr, rows, cols, col_tiles, nbands);
+  check_launch("get_col_row_stats");
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5b: double quant.  out_row = (int8)rint(x * (127/rowStat)), out_col = (int8)rint(x * (127/colStat));
+// IEEE divide, one multiply, round-half-even, saturating convert, NaN -> 0.  thr > 0: outliers get
+// out_row = 0 and a COO entry at nnz_row_ptr[tile*16 + r%16] + (rank of the column inside the segment)
+// -- ascending column order inside each (tile,row) segment, so the COO is deterministic.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int quant_s8(float x, float scale) {
+  int q = __float2int_rn(__fmul_rn(x, scale));  // NaN -> 0, saturates at int32
+  return max(-128, min(127, q));
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_double_rowcol_quant(const __half *__restrict__ A, const float *__restrict__ rowStats,
+                                                             const float *__restrict__ colStats, signed char *out_col,
+                                                             signed char *out_row, int *rowidx, int *colidx, __half *val,
+                                                             const int *__restrict__ nnz_row_ptr, float thr, int rows,
+                                                             int cols, int col_tiles, int nbands) {
+  const int lane = threadIdx.x & 31;
+  const long wid = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (wid >= (long)nbands * col_tiles) return;
+  const int band = (int)(wid / col_tiles), ct = (int)(wid % col_tiles);
+  const int c0 = ct * 256 + lane * 8;
+  const int r0 = band * kBandRows;
+  const bool sparse = thr > 0.0f;
+
+  float cscale[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) cscale[j] = (c0 + j < cols) ? __fdiv_rn(127.0f, colStats[c0 + j]) : 0.0f;
+
+  for (int rb = 0; rb < kBandRows; rb += 4) {
+    uint4 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int r = r0 + rb + u;
+      raw[u] = make_uint4(0, 0, 0, 0);
+      if (r < rows) {
+        if (VEC) {
+          if (c0 < cols) raw[u] = ld_stream_u4(A + (long)r * cols + c0);
+        } else {
+          __half *p = reinterpret_cast<__half *>(&raw[u]);
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            if (c0 + j < cols) p[j] = A[(long)r * cols + c0 + j];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int r = r0 + rb + u;
+      if (r >= rows) continue;  // warp-uniform
+      const __half *p = reinterpret_cast<const __half *>(&raw[u]);
+      const float rscale = __fdiv_rn(127.0f, __ldg(rowStats + r));
+      uint32_t qr[2] = {0, 0}, qc[2] = {0, 0};
+      uint32_t outlier_mask = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const float x = __half2float(p[j]);
+        int r8;
+        if (sparse && fabsf(x) >= thr && c0 + j < cols) { r8 = 0; outlier_mask |= 1u << j; }
+        else r8 = quant_s8(x, rscale);
+        const int c8 = quant_s8(x, cscale[j]);
+        qr[j >> 2] |= (uint32_t)(r8 & 0xFF) << (8 * (j & 3));
+        qc[j >> 2] |= (uint32_t)(c8 & 0xFF) << (8 * (j & 3));
+      }
+      const long o = (long)r * cols + c0;
+      if (VEC) {
+        if (c0 < cols) {
+          *reinterpret_cast<uint2 *>(out_row + o) = make_uint2(qr[0], qr[1]);
+          *reinterpret_cast<uint2 *>(out_col + o) = make_uint2(qc[0], qc[1]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          if (c0 + j < cols) {
+            out_row[o + j] = (signed char)(qr[j >> 2] >> (8 * (j & 3)));
+            out_col[o + j] = (signed char)(qc[j >> 2] >> (8 * (j & 3)));
+          }
+      }
+      if (sparse && rowidx != nullptr) {
+        // exclusive prefix of the per-lane outlier counts -> ascending-column slots
+        const int mine = __popc(outlier_mask);
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          int t = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += t;
+        }
+        if (mine) {
+          int slot = nnz_row_ptr[((long)(r / 16) * col_tiles + ct) * 16 + (r % 16)] + incl - mine;
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            if (outlier_mask & (1u << j)) {
+              rowidx[slot] = r;
+              colidx[slot] = c0 + j;
+              val[slot] = p[j];
+              slot++;
+            }
+        }
+      }
+    }
+  }
+}
+
+void double_rowcol_quant(const __half *A, const float *rowStats, const float *colStats, signed char *out_col,
+                         signed char *out_row, int *rowidx, int *colidx, __half *val, const int *nnz_row_ptr,
+                         float thr, int rows, int cols) {
+  if (rows <= 0 || cols <= 0) return;
+  const int col_tiles = ceil_div(cols, 256);
+  const int nbands = ceil_div(rows, kBandRows);
+  const unsigned grid = (unsigned)ceil_div_ll((long)nbands * col_tiles, 8);
+  const bool vec = (cols % 8 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(out_row) % 8 == 0) && (reinterpret_cast<uintptr_t>(out_col) % 8 == 0);
+  if (vec) k_double_rowcol_quant<true><<<grid, 256, 0, current_stream()>>>(A, rowStats, colStats, out_col, out_row, rowidx, colidx, val, nnz_row_ptr, thr, rows, cols, col_tiles, nbands);
+  else k_double_rowcol_quant<false><<<grid, 256, 0, current_stream()>>>(A, rowStats, colStats, out_col, out_row, rowidx, colidx, val, nnz_row_ptr, thr, rows, cols, col_tiles, nbands);
+  check_launch("double_rowcol_quant");
+}
+
+// ------------------------------------------------------------------------------------------------
+// layouts (kernel_quant.cpp:3673-3675, :3740-3755, :3822-3832 == blas_utils.h:263-325)
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ long layout_out_rows(int fmt, int rows) {
+  if (fmt == COL_TURING) return ((rows + 7) / 8) * 8L;
+  if (fmt == COL_AMPERE) return ((rows + 31) / 32) * 32L;
+  return rows;
+}
+__host__ __device__ __forceinline__ long layout_offset(int fmt, long out_rows, int r, int c) {
+  const int c32 = c & 31;
+  if (fmt == COL32) return (long)(c >> 5) * 32 * out_rows + (long)r * 32 + c32;
+  if (fmt == COL_TURING) {
+    long off = (long)(c >> 5) * out_rows * 32 + (long)(r >> 3) * 256 + (c32 >> 2) * 16 + (c32 & 3);
+    return off + ((r & 1) ? 128 + ((r & 7) - 1) * 2 : (r & 7) * 2);
+  }
+  const int lr = r & 31;
+  const int ar = ((lr & 7) >> 1) * 8 + (lr >> 3) * 2 + (lr & 1);
+  return (long)(c >> 5) * out_rows * 32 + (long)(r >> 5) * 1024 + ar * 32 + c32;
+}
+
+// row-major [rows, cols] -> fmt.  Each thread moves 4 consecutive columns of one row (4 consecutive
+// columns are contiguous in all three layouts); a warp covers 128 columns of a row.
+template <int FMT, typename E>
+__global__ void __launch_bounds__(256) k_transform(const E *__restrict__ A, E *__restrict__ out, int rows, int cols,
+                                                   long out_rows) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cgroups = (cols + 3) / 4;
+  if (idx >= (long)rows * cgroups) return;
+  const int r = (int)(idx / cgroups), c = (int)(idx % cgroups) * 4;
+  const E *src = A + (long)r * cols + c;
+  E *dst = out + layout_offset(FMT, out_rows, r, c);
+  if (sizeof(E) == 1 && c + 4 <= cols && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+    *reinterpret_cast<uint32_t *>(dst) = *reinterpret_cast<const uint32_t *>(src);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (c + j < cols) dst[j] = src[j];
+  }
+}
+// transposed: out = fmt(A^T).  Thread per element of A^T with the A^T column (= A row) fastest, so the
+// writes are the coalesced side.
+template <int FMT, typename E>
+__global__ void __launch_bounds__(256) k_transform_T(const E *__restrict__ A, E *__restrict__ out, int rows, int cols,
+                                                     long out_rows) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)rows * cols) return;
+  const int c = (int)(idx / rows), r = (int)(idx % rows);  // element A[r][c] == A^T[c][r]
+  out[layout_offset(FMT, out_rows, c, r)] = A[(long)r * cols + c];
+}
+
+template <int FMT>
+void transform_row2fmt(const signed char *A, signed char *out, int rows, int cols, bool transpose) {
+  if (rows <= 0 || cols <= 0) return;
+  cudaStream_t st = current_stream();
+  if (!transpose) {
+    const long n = (long)rows * ((cols + 3) / 4);
+    k_transform<FMT, signed char><<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(A, out, rows, cols, layout_out_rows(FMT, rows));
+  } else {
+    const long n = (long)rows * cols;
+    k_transform_T<FMT, signed char><<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(A, out, rows, cols, layout_out_rows(FMT, cols));
+  }
+  check_launch("transform_row2fmt");
+}
+template void transform_row2fmt<COL32>(const signed char *, signed char *, int, int, bool);
+template void transform_row2fmt<COL_TURING>(const signed char *, signed char *, int, int, bool);
+template void transform_row2fmt<COL_AMPERE>(const signed char *, signed char *, int, int, bool);
+
+// fmt -> row-major (used by the cigemmlt_* ABI wrappers to feed the row-major tcgen05 GEMM)
+template <int FMT, typename E>
+__global__ void __launch_bounds__(256) k_untransform(const E *__restrict__ A, E *__restrict__ out, int rows, int cols,
+                                                     long in_rows) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cgroups = (cols + 3) / 4;
+  if (idx >= (long)rows * cgroups) return;
+  const int r = (int)(idx / cgroups), c = (int)(idx % cgroups) * 4;
+  const E *src = A + layout_offset(FMT, in_rows, r, c);
+  E *dst = out + (long)r * cols + c;
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+    if (c + j < cols) dst[j] = src[j];
+}
+void untransform_s8(int fmt, const signed char *A, signed char *out, int rows, int cols) {
+  const long n = (long)rows * ((cols + 3) / 4);
+  const unsigned grid = (unsigned)ceil_div_ll(n, 256);
+  cudaStream_t st = current_stream();
+  if (fmt == COL32) k_untransform<COL32, signed char><<<grid, 256, 0, st>>>(A, out, rows, cols, layout_out_rows(COL32, rows));
+  else if (fmt == COL_TURING) k_untransform<COL_TURING, signed char><<<grid, 256, 0, st>>>(A, out, rows, cols, layout_out_rows(COL_TURING, rows));
+  else k_untransform<COL_AMPERE, signed char><<<grid, 256, 0, st>>>(A, out, rows, cols, layout_out_rows(COL_AMPERE, rows));
+  check_launch("untransform_s8");
+}
+// row-major int32 / int8 -> col32 (C operand of the cigemmlt_* ABI)
+template <typename E>
+void to_col32(const E *A, E *out, int rows, int cols) {
+  const long n = (long)rows * ((cols + 3) / 4);
+  k_transform<COL32, E><<<(unsigned)ceil_div_ll(n, 256), 256, 0, current_stream()>>>(A, out, rows, cols, rows);
+  check_launch("to_col32");
+}
+template void to_col32<int>(const int *, int *, int, int);
+template void to_col32<signed char>(const signed char *, signed char *, int, int);
+
+// ------------------------------------------------------------------------------------------------
+// K7: outlier column gather out[row, j] = A_fmt(row, idx[j])
+// ------------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(256) k_extract_outliers(const signed char *__restrict__ A, const int *__restrict__ idx,
+                                                          signed char *__restrict__ out, int idx_size, int rows,
+                                                          long fmt_rows) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)rows * idx_size) return;
+  const int r = (int)(i / idx_size), j = (int)(i % idx_size);
+  out[i] = A[layout_offset(FMT, fmt_rows, r, idx[j])];
+}
+template <int FMT>
+void extract_outliers(const signed char *A, const int *idx, signed char *out, int idx_size, int rows, int cols) {
+  (void)cols;
+  if (rows <= 0 || idx_size <= 0) return;
+  const long n = (long)rows * idx_size;
+  k_extract_outliers<FMT><<<(unsigned)ceil_div_ll(n, 256), 256, 0, current_stream()>>>(A, idx, out, idx_size, rows, layout_out_rows(FMT, rows));
+  check_launch("extract_outliers");
+}
+template void extract_outliers<COL_TURING>(const signed char *, const int *, signed char *, int, int, int);
+template void extract_outliers<COL_AMPERE>(const signed char *, const int *, signed char *, int, int, int);
+
+// ------------------------------------------------------------------------------------------------
+// a9: int32 (col32) -> fp16 row-major, out = half(((float(c) * K) * rowStat) * colStat + bias);
+// four fp32 operations in the reference's order, no contraction.
+// A lane owns 4 consecutive columns of one row: 128-bit load from the col32 tile, 64-bit store.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dequant_one(int c, float rs, float cs, float b) {
+  float t = __fmul_rn(__int2float_rn(c), kMMDequantConst);
+  t = __fmul_rn(t, rs);
+  t = __fmul_rn(t, cs);
+  return __fadd_rn(t, b);
+}
+
+__global__ void __launch_bounds__(256) k_dequant_mm_int32_fp16(const int *__restrict__ A, const float *__restrict__ rowStats,
+                                                               const float *__restrict__ colStats, __half *__restrict__ out,
+                                                               const __half *__restrict__ bias, int numRows, int numCols) {
+  // work item = (col group of 32, row, quad of 4 columns); quads fastest, then rows: a warp covers
+  // 4 rows x 32 columns = 4 x 128 contiguous bytes of the col32 tile
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cgroups = (numCols + 31) / 32;
+  if (idx >= (long)cgroups * numRows * 8) return;
+  const int quad = (int)(idx & 7);
+  const long t = idx >> 3;
+  const int r = (int)(t % numRows);
+  const int cg = (int)(t / numRows);
+  const int c = cg * 32 + quad * 4;
+  if (c >= numCols) return;
+  const int4 v = *reinterpret_cast<const int4 *>(A + ((long)cg * numRows + r) * 32 + quad * 4);
+  const float rs = __ldg(rowStats + r);
+  const int vals[4] = {v.x, v.y, v.z, v.w};
+  __half h[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int cc = c + j;
+    const float cs = cc < numCols ? __ldg(colStats + cc) : 0.0f;
+    const float b = (bias != nullptr && cc < numCols) ? __half2float(bias[cc]) : 0.0f;
+    h[j] = __float2half_rn(dequant_one(vals[j], rs, cs, b));
+  }
+  __half *dst = out + (long)r * numCols + c;
+  if (c + 4 <= numCols && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+    *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(h);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (c + j < numCols) dst[j] = h[j];
+  }
+}
+
+void dequant_mm_int32_fp16(const int *A, const float *rowStats, const float *colStats, __half *out, const __half *bias,
+                           int numRows, int numCols) {
+  if (numRows <= 0 || numCols <= 0) return;
+  const long n = (long)((numCols + 31) / 32) * numRows * 8;
+  k_dequant_mm_int32_fp16<<<(unsigned)ceil_div_ll(n, 256), 256, 0, current_stream()>>>(A, rowStats, colStats, out, bias, numRows, numCols);
+  check_launch("dequant_mm_int32_fp16");
+}
+
+}  // namespace bnb

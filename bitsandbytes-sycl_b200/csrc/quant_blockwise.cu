@@ -1,0 +1,423 @@
+// quant_blockwise.cu -- K1/K2: blockwise quantize / dequantize (NF4, FP4, 8-bit code) for sm_100a.
+//
+// Replaces kQuantizeBlockwise / kDequantizeBlockwise (reference sycl/sycl_code/kernel_quant.cpp:1229-1471,
+// launchers op_quant.cpp:431-703).  Both are pure HBM streams; design:
+//   * 128-bit coalesced global accesses, one vector per lane, U vectors in flight per lane;
+//   * a quantisation block (64..4096 elements) lives in a power-of-two group of lanes (or whole warp
+//     rows), absmax by __shfl_xor -- no shared memory, no barriers in the hot loop;
+//   * arithmetic chain identical to the reference: absmax = max|x| (fp32), inv = 1.0f / absmax (IEEE
+//     divide), xn = x * inv (one rounding), code(xn) == the reference's decision tree, NaN -> 0;
+//   * the 4-bit decision tree is evaluated through a 1/64-cell lookup (one 16-byte shared-memory
+//     load, conflict-free for any address pattern only per phase) that is proven equal to the
+//     tree for EVERY float by cbnb_selftest_quant_lut().
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <mutex>
+
+#include "codebooks.cuh"
+#include "common.cuh"
+
+namespace bnb {
+
+// ------------------------------------------------------------------------------------------------
+// 4-bit quantize LUT
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) QCell {
+  float thr;
+  uint32_t lo;
+  uint32_t hi;
+  uint32_t pad;
+};
+constexpr int kQCells = 256;
+__device__ QCell g_qlut[2][kQCells];        // [0] = FP4 (indexed by |x|), [1] = NF4
+__device__ float g_dq4_table[2][16];        // [0] = FP4, [1] = NF4 dequant values
+static QCell h_qlut[2][kQCells];
+static float h_dq4[2][16];
+static std::once_flag h_lut_once;
+static bool g_lut_ready[64] = {false};
+static std::mutex g_lut_mutex;
+
+// cell c holds floats x with RNE(x*1024 + 1024) in [16c, 16c+15]; built with a one-unit safety margin
+static void build_cells(QCell *cells, const float *thr, int nthr, const int *bucket_codes) {
+  for (int c = 0; c < kQCells; c++) {
+    double lo_x = (16.0 * c - 1.0 - 1024.0) / 1024.0;
+    double hi_x = (16.0 * c + 16.0 - 1024.0) / 1024.0;
+    int nbelow = 0, inside = -1, ninside = 0;
+    for (int j = 0; j < nthr; j++) {
+      if ((double)thr[j] < lo_x) nbelow++;
+      else if ((double)thr[j] <= hi_x) { inside = j; ninside++; }
+    }
+    if (ninside > 1) { fprintf(stderr, "bnb_b200: quantize LUT cell holds two thresholds\n"); abort(); }
+    if (ninside == 1) {
+      cells[c].thr = thr[inside];
+      cells[c].lo = (uint32_t)bucket_codes[inside];
+      cells[c].hi = (uint32_t)bucket_codes[inside + 1];
+    } else {
+      cells[c].thr = INFINITY;
+      cells[c].lo = cells[c].hi = (uint32_t)bucket_codes[nbelow];
+    }
+    cells[c].pad = 0;
+  }
+}
+
+static void build_host_tables() {
+  static const float nf4_thr[15] = BNB_NF4_THRESHOLDS;
+  static const float fp4_thr[7] = BNB_FP4_THRESHOLDS;
+  static const int fp4_codes[8] = BNB_FP4_BUCKET_CODES;
+  static const float nf4_tab[16] = BNB_NF4_TABLE;
+  static const float fp4_mag[8] = BNB_FP4_MAGNITUDES;
+  int nf4_codes[16];
+  for (int i = 0; i < 16; i++) nf4_codes[i] = i;
+  build_cells(h_qlut[1], nf4_thr, 15, nf4_codes);
+  build_cells(h_qlut[0], fp4_thr, 7, fp4_codes);
+  for (int i = 0; i < 16; i++) h_dq4[1][i] = nf4_tab[i];
+  for (int i = 0; i < 8; i++) { h_dq4[0][i] = fp4_mag[i]; h_dq4[0][i + 8] = -fp4_mag[i]; }
+}
+
+// upload the tables to the current device once (per device)
+void ensure_tables() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && g_lut_ready[dev]) return;
+  std::lock_guard<std::mutex> lock(g_lut_mutex);
+  if (dev < 64 && g_lut_ready[dev]) return;
+  std::call_once(h_lut_once, build_host_tables);
+  latch_error(cudaMemcpyToSymbol(g_qlut, h_qlut, sizeof(h_qlut)), "upload quantize LUT");
+  latch_error(cudaMemcpyToSymbol(g_dq4_table, h_dq4, sizeof(h_dq4)), "upload dequant table");
+  if (dev < 64) g_lut_ready[dev] = true;
+}
+
+template <int QT>
+__device__ __forceinline__ uint32_t quantize4_lut(float xn, const QCell *lut) {
+  float ax = (QT == FP4) ? fabsf(xn) : xn;
+  float cl = fminf(fmaxf(ax, -1.0f), 1.0f);  // +-inf (denormal absmax) -> +-1: same bucket as the tree
+  uint32_t off = __float_as_uint(__fmaf_rn(cl, 1024.0f, 12583936.0f)) & 0xFF0u;  // 1.5*2^23 + 1024
+  const QCell c = *reinterpret_cast<const QCell *>(reinterpret_cast<const char *>(lut) + off);
+  uint32_t code = ax > c.thr ? c.hi : c.lo;
+  if (QT == FP4) code |= (xn < 0.0f) ? 8u : 0u;
+  return (xn != xn) ? 0u : code;  // every compare of the tree is false for NaN -> code 0
+}
+
+template <int QT>
+__device__ __forceinline__ uint32_t quantize_one(float xn, const QCell *lut, const float *code) {
+  if (QT == General8bit) return quantize_8bit_search(code, xn);
+  return quantize4_lut<QT>(xn, lut);
+}
+
+// ------------------------------------------------------------------------------------------------
+// vector load of E elements of T as fp32, zero-filled past n
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool ALIGNED>
+__device__ __forceinline__ void load_vec(const T *A, long e0, long n, float (&x)[16 / sizeof(T)]) {
+  constexpr int E = 16 / sizeof(T);
+  if (ALIGNED && e0 + E <= n) {
+    uint4 raw = ld_stream_u4(A + e0);
+    const T *p = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+    for (int j = 0; j < E; j++) x[j] = to_float<T>(p[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < E; j++) x[j] = (e0 + j < n) ? to_float<T>(A[e0 + j]) : 0.0f;
+  }
+}
+
+// quantise E normalised values and store them (4-bit: E/2 bytes, 8-bit: E bytes)
+template <typename T, int QT, bool ALIGNED>
+__device__ __forceinline__ void quantize_store(const float (&x)[16 / sizeof(T)], float inv, long e0, long n,
+                                               unsigned char *out, const QCell *lut, const float *code) {
+  constexpr int E = 16 / sizeof(T);
+  if (e0 >= n) return;
+  if (QT == General8bit) {
+    uint32_t w[E / 4];
+#pragma unroll
+    for (int j = 0; j < E / 4; j++) {
+      uint32_t b0 = quantize_one<QT>(__fmul_rn(x[4 * j + 0], inv), lut, code);
+      uint32_t b1 = quantize_one<QT>(__fmul_rn(x[4 * j + 1], inv), lut, code);
+      uint32_t b2 = quantize_one<QT>(__fmul_rn(x[4 * j + 2], inv), lut, code);
+      uint32_t b3 = quantize_one<QT>(__fmul_rn(x[4 * j + 3], inv), lut, code);
+      w[j] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    }
+    if (ALIGNED && e0 + E <= n) {
+      if (E == 4) *reinterpret_cast<uint32_t *>(out + e0) = w[0];
+      else *reinterpret_cast<uint2 *>(out + e0) = make_uint2(w[0], w[E / 4 - 1]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < E; j++)
+        if (e0 + j < n) out[e0 + j] = (unsigned char)(w[j / 4] >> (8 * (j % 4)));
+    }
+  } else {
+    uint32_t packed = 0;
+#pragma unroll
+    for (int j = 0; j < E / 2; j++) {
+      uint32_t hi = quantize_one<QT>(__fmul_rn(x[2 * j], inv), lut, code);
+      uint32_t lo = quantize_one<QT>(__fmul_rn(x[2 * j + 1], inv), lut, code);
+      packed |= ((hi << 4) | lo) << (8 * j);
+    }
+    unsigned char *dst = out + (e0 >> 1);
+    if (ALIGNED && e0 + E <= n) {
+      if (E == 4) *reinterpret_cast<uint16_t *>(dst) = (uint16_t)packed;
+      else *reinterpret_cast<uint32_t *>(dst) = packed;
+    } else {
+#pragma unroll
+      for (int j = 0; j < E / 2; j++)
+        if (e0 + 2 * j < n) dst[j] = (unsigned char)(packed >> (8 * j));
+    }
+  }
+}
+
+template <int QT>
+__device__ __forceinline__ void stage_tables(QCell *s_lut, float *s_code, const float *code) {
+  if (QT == General8bit) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_code[i] = code[i];
+  } else {
+    const QCell *src = g_qlut[QT == NF4 ? 1 : 0];
+    for (int i = threadIdx.x; i < kQCells; i += blockDim.x) s_lut[i] = src[i];
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1a: blocksize <= 32*E -- a block is a group of G = blocksize/E lanes inside one warp row
+// ------------------------------------------------------------------------------------------------
+template <typename T, int QT, bool ALIGNED>
+__global__ void __launch_bounds__(256) k_quantize_small(const float *__restrict__ code, const T *__restrict__ A,
+                                                        float *__restrict__ absmax, unsigned char *__restrict__ out,
+                                                        int blocksize, long n) {
+  constexpr int E = 16 / sizeof(T);
+  constexpr int U = 4;
+  __shared__ QCell s_lut[QT == General8bit ? 1 : kQCells];
+  __shared__ float s_code[QT == General8bit ? 256 : 1];
+  stage_tables<QT>(s_lut, s_code, code);
+
+  const int lane = threadIdx.x & 31;
+  const long warp_global = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long v0 = warp_global * U * 32 + lane;
+  const int G = blocksize / E;
+
+  float x[U][E];
+#pragma unroll
+  for (int u = 0; u < U; u++) load_vec<T, ALIGNED>(A, (v0 + u * 32) * E, n, x[u]);
+
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const long e0 = (v0 + u * 32) * E;
+    float m = -FLT_MAX;
+#pragma unroll
+    for (int j = 0; j < E; j++) m = fmaxf(m, fabsf(x[u][j]));
+    for (int o = G >> 1; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((lane & (G - 1)) == 0 && e0 < n) absmax[e0 / blocksize] = m;
+    const float inv = __fdiv_rn(1.0f, m);
+    quantize_store<T, QT, ALIGNED>(x[u], inv, e0, n, out, s_lut, s_code);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1b: blocksize > 32*E -- one warp per block, two passes (second pass re-reads through L1/L2)
+// ------------------------------------------------------------------------------------------------
+template <typename T, int QT, bool ALIGNED>
+__global__ void __launch_bounds__(256) k_quantize_large(const float *__restrict__ code, const T *__restrict__ A,
+                                                        float *__restrict__ absmax, unsigned char *__restrict__ out,
+                                                        int blocksize, long n, long nblocks) {
+  constexpr int E = 16 / sizeof(T);
+  __shared__ QCell s_lut[QT == General8bit ? 1 : kQCells];
+  __shared__ float s_code[QT == General8bit ? 256 : 1];
+  stage_tables<QT>(s_lut, s_code, code);
+
+  const int lane = threadIdx.x & 31;
+  const long block = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (block >= nblocks) return;
+  const int R = blocksize / (32 * E);
+  const long ebase = block * blocksize;
+
+  float m = -FLT_MAX;
+  for (int r = 0; r < R; r++) {
+    float x[E];
+    load_vec<T, ALIGNED>(A, ebase + ((long)r * 32 + lane) * E, n, x);
+#pragma unroll
+    for (int j = 0; j < E; j++) m = fmaxf(m, fabsf(x[j]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) absmax[block] = m;
+  const float inv = __fdiv_rn(1.0f, m);
+  for (int r = 0; r < R; r++) {
+    float x[E];
+    const long e0 = ebase + ((long)r * 32 + lane) * E;
+    load_vec<T, ALIGNED>(A, e0, n, x);
+    quantize_store<T, QT, ALIGNED>(x, inv, e0, n, out, s_lut, s_code);
+  }
+}
+
+template <typename T, int QT>
+void quantize_blockwise(const float *code, const T *A, float *absmax, unsigned char *out, int blocksize, long n) {
+  if (n <= 0) return;
+  constexpr int E = 16 / sizeof(T);
+  if (blocksize < 64 || (blocksize & (blocksize - 1)) != 0 || blocksize > 4096) {
+    latch_error(cudaErrorInvalidValue, "quantize_blockwise: blocksize must be a power of two in [64, 4096]");
+    return;
+  }
+  if (QT != General8bit) ensure_tables();
+  cudaStream_t st = current_stream();
+  const bool aligned = (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 8 == 0);
+  if (blocksize <= 32 * E) {
+    const long nvec = ceil_div_ll(n, E);
+    const long nwarps = ceil_div_ll(nvec, 32 * 4);
+    const unsigned grid = (unsigned)ceil_div_ll(nwarps, 8);
+    if (aligned) k_quantize_small<T, QT, true><<<grid, 256, 0, st>>>(code, A, absmax, out, blocksize, n);
+    else k_quantize_small<T, QT, false><<<grid, 256, 0, st>>>(code, A, absmax, out, blocksize, n);
+  } else {
+    const long nblocks = ceil_div_ll(n, blocksize);
+    const unsigned grid = (unsigned)ceil_div_ll(nblocks, 8);
+    if (aligned) k_quantize_large<T, QT, true><<<grid, 256, 0, st>>>(code, A, absmax, out, blocksize, n, nblocks);
+    else k_quantize_large<T, QT, false><<<grid, 256, 0, st>>>(code, A, absmax, out, blocksize, n, nblocks);
+  }
+  check_launch("quantize_blockwise");
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: dequantize.  out[i] = T(table[q_i] * absmax[i / blocksize]) -- fp32 multiply, one rounding.
+// Each lane turns E/2 packed bytes (4-bit) or E bytes (8-bit) into one 128-bit store.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int QT, bool ALIGNED>
+__global__ void __launch_bounds__(256) k_dequantize(const float *__restrict__ code, const unsigned char *__restrict__ A,
+                                                    const float *__restrict__ absmax, T *__restrict__ out,
+                                                    int blocksize, int bs_shift, long n) {
+  constexpr int E = 16 / sizeof(T);
+  constexpr int U = 8;
+  __shared__ float s_tab[QT == General8bit ? 256 : 16];
+  if (QT == General8bit) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = code[i];
+  } else if (threadIdx.x < 16) {
+    s_tab[threadIdx.x] = g_dq4_table[QT == NF4 ? 1 : 0][threadIdx.x];
+  }
+  __syncthreads();
+
+  const long vcta = (long)blockIdx.x * (256 * U);
+  uint32_t raw[U][2];
+  float am[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const long e0 = (vcta + u * 256 + threadIdx.x) * E;
+    raw[u][0] = raw[u][1] = 0;
+    am[u] = 0.0f;
+    if (e0 < n) {
+      am[u] = __ldg(absmax + (bs_shift >= 0 ? (e0 >> bs_shift) : (e0 / blocksize)));
+      if (QT == General8bit) {
+        if (ALIGNED && e0 + E <= n) {
+          if (E == 4) raw[u][0] = ld_stream_u1(A + e0);
+          else { uint2 t = ld_stream_u2(A + e0); raw[u][0] = t.x; raw[u][1] = t.y; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < E; j++)
+            if (e0 + j < n) raw[u][j / 4] |= (uint32_t)A[e0 + j] << (8 * (j % 4));
+        }
+      } else {
+        const unsigned char *src = A + (e0 >> 1);
+        if (ALIGNED && e0 + E <= n) {
+          if (E == 4) raw[u][0] = *reinterpret_cast<const uint16_t *>(src);
+          else raw[u][0] = ld_stream_u1(src);
+        } else {
+#pragma unroll
+          for (int j = 0; j < E / 2; j++)
+            if (e0 + 2 * j < n) raw[u][0] |= (uint32_t)src[j] << (8 * j);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const long e0 = (vcta + u * 256 + threadIdx.x) * E;
+    if (e0 >= n) continue;
+    float v[E];
+#pragma unroll
+    for (int j = 0; j < E; j++) {
+      uint32_t q;
+      if (QT == General8bit) q = (raw[u][j / 4] >> (8 * (j % 4))) & 0xFFu;
+      else q = (raw[u][0] >> (8 * (j / 2) + ((j & 1) ? 0 : 4))) & 0xFu;  // even element = high nibble
+      v[j] = __fmul_rn(s_tab[q], am[u]);
+    }
+    if (ALIGNED && e0 + E <= n) {
+      uint4 pk;
+      T *p = reinterpret_cast<T *>(&pk);
+#pragma unroll
+      for (int j = 0; j < E; j++) p[j] = from_float<T>(v[j]);
+      st_stream_u4(out + e0, pk);
+    } else {
+#pragma unroll
+      for (int j = 0; j < E; j++)
+        if (e0 + j < n) out[e0 + j] = from_float<T>(v[j]);
+    }
+  }
+}
+
+template <typename T, int QT>
+void dequantize_blockwise(const float *code, const unsigned char *A, const float *absmax, T *out, int blocksize, long n) {
+  if (n <= 0) return;
+  constexpr int E = 16 / sizeof(T);
+  if (blocksize <= 0) { latch_error(cudaErrorInvalidValue, "dequantize_blockwise: blocksize"); return; }
+  if (QT != General8bit) ensure_tables();
+  int bs_shift = -1;
+  if ((blocksize & (blocksize - 1)) == 0) { bs_shift = 0; while ((1 << bs_shift) < blocksize) bs_shift++; }
+  if (blocksize < E) bs_shift = -2;  // a vector would straddle blocks: not a supported configuration
+  if (bs_shift == -2 || (bs_shift == -1 && blocksize % E != 0)) {
+    latch_error(cudaErrorInvalidValue, "dequantize_blockwise: blocksize must be a multiple of 8");
+    return;
+  }
+  const bool aligned = (reinterpret_cast<uintptr_t>(out) % 16 == 0) && (reinterpret_cast<uintptr_t>(A) % 8 == 0);
+  const long nvec = ceil_div_ll(n, E);
+  const unsigned grid = (unsigned)ceil_div_ll(nvec, 256 * 8);
+  cudaStream_t st = current_stream();
+  if (aligned) k_dequantize<T, QT, true><<<grid, 256, 0, st>>>(code, A, absmax, out, blocksize, bs_shift, n);
+  else k_dequantize<T, QT, false><<<grid, 256, 0, st>>>(code, A, absmax, out, blocksize, bs_shift, n);
+  check_launch("dequantize_blockwise");
+}
+
+// ------------------------------------------------------------------------------------------------
+// exhaustive self-test: LUT quantiser == reference tree for every fp32 bit pattern
+// ------------------------------------------------------------------------------------------------
+template <int QT>
+__global__ void k_selftest_lut(unsigned long long *mismatches) {
+  __shared__ QCell s_lut[kQCells];
+  stage_tables<QT>(s_lut, nullptr, nullptr);
+  unsigned long long bad = 0;
+  const unsigned long long total = 1ull << 32;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    float x = __uint_as_float((uint32_t)i);
+    uint32_t a = quantize4_lut<QT>(x, s_lut);
+    uint32_t b = (QT == NF4) ? quantize_nf4_tree(x) : quantize_fp4_tree(x);
+    bad += (a != b);
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+long long selftest_quant_lut(int qtype) {
+  ensure_tables();
+  unsigned long long *d = nullptr, h = 0;
+  if (cudaMalloc(&d, sizeof(h)) != cudaSuccess) return -1;
+  cudaMemset(d, 0, sizeof(h));
+  if (qtype == NF4) k_selftest_lut<NF4><<<kNumSMs * 8, 256, 0, current_stream()>>>(d);
+  else k_selftest_lut<FP4><<<kNumSMs * 8, 256, 0, current_stream()>>>(d);
+  check_launch("selftest_quant_lut");
+  cudaStreamSynchronize(current_stream());
+  cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return (long long)h;
+}
+
+// explicit instantiations used by c_api.cu
+#define INST(T)                                                                                               \
+  template void quantize_blockwise<T, General8bit>(const float *, const T *, float *, unsigned char *, int, long); \
+  template void quantize_blockwise<T, FP4>(const float *, const T *, float *, unsigned char *, int, long);     \
+  template void quantize_blockwise<T, NF4>(const float *, const T *, float *, unsigned char *, int, long);     \
+  template void dequantize_blockwise<T, General8bit>(const float *, const unsigned char *, const float *, T *, int, long); \
+  template void dequantize_blockwise<T, FP4>(const float *, const unsigned char *, const float *, T *, int, long); \
+  template void dequantize_blockwise<T, NF4>(const float *, const unsigned char *, const float *, T *, int, long);
+INST(float)
+INST(__half)
+INST(__nv_bfloat16)
+#undef INST
+
+}  // namespace bnb

@@ -1,0 +1,141 @@
+/*
+ * bnb_b200.h -- C-ABI of libbitsandbytes_b200.so, the B200 (sm_100a) drop-in for the quantized-linear
+ * hot path of abhilash1910/bitsandbytes-SYCL.
+ *
+ * Every entry point in section 1 has the EXACT name, argument order and argument meaning of the
+ * symbol the reference exports from sycl/pythonInterface.cpp (file:line cited per group) and that
+ * python_src_quants/functional.py binds through ctypes (python_src_quants/cextension.py:88-110).
+ * Conventions, kept as in the reference:
+ *   - plain C, raw DEVICE pointers, 32-bit ints / floats by value, NULL allowed where the reference
+ *     passes None; every buffer is allocated and owned by the caller; the library never frees or
+ *     allocates user-visible memory;
+ *   - launches are asynchronous on the caller's current device; the ABI has no stream slot, so the
+ *     launch stream is a thread-local set with cbnb_set_stream() (default: the legacy default
+ *     stream 0 == PyTorch's default stream, so an un-patched caller stays correct);
+ *   - `void` functions report nothing (errors are latched, see cbnb_last_error()); cigemmlt_*
+ *     return int: 0 ok, 1 -> the reference's Python turns it into NotImplementedError,
+ *     anything else -> "cublasLt ran into an error!" (functional.py:2341-2348).
+ * `half` / `bf16` pointers are 16-bit IEEE binary16 / bfloat16 device arrays (typed `void*` here so
+ * the header is plain C).
+ *
+ * Section 2 lists the ADDITIVE symbols (same convention) that exist only in this library.
+ */
+#ifndef BNB_B200_H
+#define BNB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNB_B200_API __attribute__((visibility("default")))
+
+/* ============================== 1. reference ABI (hot-path subset) ============================== */
+
+/* --- blockwise quantize: sycl/pythonInterface.cpp:203-217 (kQuantizeBlockwise, kernel_quant.cpp:1229)
+ * code: 256-entry fp32 map (General8bit) or NULL (fp4/nf4); A: n elements of T; absmax: ceil(n/blocksize)
+ * fp32; out: n bytes (8-bit) or (n+1)/2 bytes (4-bit, even element in the high nibble);
+ * blocksize in {64,128,256,512,1024,2048,4096}. */
+BNB_B200_API void cquantize_blockwise_fp32(float *code, float *A, float *absmax, unsigned char *out, int blocksize, const int n);
+BNB_B200_API void cquantize_blockwise_fp32_fp4(float *code, float *A, float *absmax, unsigned char *out, int blocksize, const int n);
+BNB_B200_API void cquantize_blockwise_fp32_nf4(float *code, float *A, float *absmax, unsigned char *out, int blocksize, const int n);
+BNB_B200_API void cquantize_blockwise_fp16(float *code, void *A, float *absmax, unsigned char *out, int blocksize, const int n);
+BNB_B200_API void cquantize_blockwise_fp16_fp4(float *code, void *A, float *absmax, unsigned char *out, int blocksize, const int n);
+BNB_B200_API void cquantize_blockwise_fp16_nf4(float *code, void *A, float *absmax, unsigned char *out, int blocksize, const int n);
+BNB_B200_API void cquantize_blockwise_bf16(float *code, void *A, float *absmax, unsigned char *out, int blocksize, const int n);
+BNB_B200_API void cquantize_blockwise_bf16_fp4(float *code, void *A, float *absmax, unsigned char *out, int blocksize, const int n);
+BNB_B200_API void cquantize_blockwise_bf16_nf4(float *code, void *A, float *absmax, unsigned char *out, int blocksize, const int n);
+
+/* --- blockwise dequantize: sycl/pythonInterface.cpp:199-221 (kDequantizeBlockwise, kernel_quant.cpp:1370)
+ * n = number of OUTPUT elements (4-bit: A holds (n+1)/2 bytes). */
+BNB_B200_API void cdequantize_blockwise_fp32(float *code, unsigned char *A, float *absmax, float *out, int blocksize, const int n);
+BNB_B200_API void cdequantize_blockwise_fp32_fp4(float *code, unsigned char *A, float *absmax, float *out, int blocksize, const int n);
+BNB_B200_API void cdequantize_blockwise_fp32_nf4(float *code, unsigned char *A, float *absmax, float *out, int blocksize, const int n);
+BNB_B200_API void cdequantize_blockwise_fp16(float *code, unsigned char *A, float *absmax, void *out, int blocksize, const int n);
+BNB_B200_API void cdequantize_blockwise_fp16_fp4(float *code, unsigned char *A, float *absmax, void *out, int blocksize, const int n);
+BNB_B200_API void cdequantize_blockwise_fp16_nf4(float *code, unsigned char *A, float *absmax, void *out, int blocksize, const int n);
+BNB_B200_API void cdequantize_blockwise_bf16(float *code, unsigned char *A, float *absmax, void *out, int blocksize, const int n);
+BNB_B200_API void cdequantize_blockwise_bf16_fp4(float *code, unsigned char *A, float *absmax, void *out, int blocksize, const int n);
+BNB_B200_API void cdequantize_blockwise_bf16_nf4(float *code, unsigned char *A, float *absmax, void *out, int blocksize, const int n);
+
+/* --- batch-1 4-bit GEMV: sycl/pythonInterface.cpp:408-415 (kgemm_4bit_inference_naive, kernel_gemm.cpp:1273)
+ * m = output features N, n = 1, k = K; A: [1,K] T; B: packed [N, ldb] bytes (ldb = (K+1)/2);
+ * absmax: fp32 [N*K/blocksize] (already de-nested); datatype: fp32[16] code; out: [1,N] T. */
+BNB_B200_API void cgemm_4bit_inference_naive_fp16(int m, int n, int k, void *A, unsigned char *B, float *absmax, float *datatype, void *out, int lda, int ldb, int ldc, int blocksize);
+BNB_B200_API void cgemm_4bit_inference_naive_bf16(int m, int n, int k, void *A, unsigned char *B, float *absmax, float *datatype, void *out, int lda, int ldb, int ldc, int blocksize);
+BNB_B200_API void cgemm_4bit_inference_naive_fp32(int m, int n, int k, float *A, unsigned char *B, float *absmax, float *datatype, float *out, int lda, int ldb, int ldc, int blocksize);
+
+/* --- LLM.int8 statistics + double quant: sycl/pythonInterface.cpp:335-339
+ * (kgetColRowStats kernel_quant.cpp:3214, kDoubleRowColQuant :3384). A: fp16 [rows, cols] row-major. */
+BNB_B200_API void cget_col_row_stats(void *A, float *rowStats, float *colStats, int *nnz_count_row, float nnz_threshold, int rows, int cols);
+BNB_B200_API void cdouble_rowcol_quant(void *A, float *rowStats, float *colStats, char *out_col_normed, char *out_row_normed, int *rowidx, int *colidx, void *val, int *nnz_row_ptr, float threshold, int rows, int cols);
+
+/* --- int8 layout transforms: sycl/pythonInterface.cpp:341-357 (kTransformRowToFormat, kernel_quant.cpp:3516).
+ * Only valid elements are written; padding comes from the caller's zeroed buffer (functional.py:482-518). */
+BNB_B200_API void ctransform_row2col32(char *A, char *out, int rows, int cols);
+BNB_B200_API void ctransform_row2col32T(char *A, char *out, int rows, int cols);
+BNB_B200_API void ctransform_row2turing(char *A, char *out, int rows, int cols);
+BNB_B200_API void ctransform_row2turingT(char *A, char *out, int rows, int cols);
+BNB_B200_API void ctransform_row2ampere(char *A, char *out, int rows, int cols);
+BNB_B200_API void ctransform_row2ampereT(char *A, char *out, int rows, int cols);
+
+/* --- int8 GEMM C = A * B^T: sycl/pythonInterface.cpp:298-316 (igemmlt, op_gemm.cpp:541-655).
+ * A: int8 col32 [m,k] (lda = m*32); B: int8 col_turing / col_ampere [n,k]; C: col32 [m,n] (ldc = m*32),
+ * int32 for *_32, saturated int8 for *_8 (alpha = 1.0f) and *_8_rowscale (alpha = row_scale[i]). */
+BNB_B200_API int cigemmlt_turing_32(int m, int n, int k, const int8_t *A, const int8_t *B, void *C, float *row_scale, int lda, int ldb, int ldc);
+BNB_B200_API int cigemmlt_turing_8(int m, int n, int k, const int8_t *A, const int8_t *B, void *C, float *row_scale, int lda, int ldb, int ldc);
+BNB_B200_API int cigemmlt_turing_8_rowscale(int m, int n, int k, const int8_t *A, const int8_t *B, void *C, float *row_scale, int lda, int ldb, int ldc);
+BNB_B200_API int cigemmlt_ampere_32(int m, int n, int k, const int8_t *A, const int8_t *B, void *C, float *row_scale, int lda, int ldb, int ldc);
+BNB_B200_API int cigemmlt_ampere_8(int m, int n, int k, const int8_t *A, const int8_t *B, void *C, float *row_scale, int lda, int ldb, int ldc);
+BNB_B200_API int cigemmlt_ampere_8_rowscale(int m, int n, int k, const int8_t *A, const int8_t *B, void *C, float *row_scale, int lda, int ldb, int ldc);
+
+/* --- int32 -> fp16 dequant: sycl/pythonInterface.cpp:333 (kdequant_mm_int32_fp16, kernel_quant.cpp:3848).
+ * A: int32 col32 [numRows, numCols]; out: fp16 row-major; newRowStats/newcolStats accepted, never written. */
+BNB_B200_API void cdequant_mm_int32_fp16(int *A, float *rowStats, float *colStats, void *out, float *newRowStats, float *newcolStats, void *bias, int numRows, int numCols);
+
+/* --- outlier column gather: sycl/pythonInterface.cpp:368-369 (kExtractOutliers, kernel_quant.cpp:3992) */
+BNB_B200_API void cextractOutliers_turing(char *A, int *idx, char *out, int idx_size, int rows, int cols);
+BNB_B200_API void cextractOutliers_ampere(char *A, int *idx, char *out, int idx_size, int rows, int cols);
+
+/* --- context: sycl/pythonInterface.cpp:295; presence of this symbol marks the library GPU-capable
+ * (python_src_quants/cextension.py:103). Returns a leaked opaque handle, as the reference does. */
+BNB_B200_API void *get_context(void);
+
+/* ============================== 2. additive symbols (this library only) ============================== */
+
+/* launch stream for the calling thread (cudaStream_t as void*); NULL = legacy default stream */
+BNB_B200_API void cbnb_set_stream(void *stream);
+BNB_B200_API void *cbnb_get_stream(void);
+/* last CUDA error latched by any entry point on this thread (0 = cudaSuccess); clears the latch */
+BNB_B200_API int cbnb_last_error(void);
+BNB_B200_API const char *cbnb_last_error_string(void);
+/* library identification: "bnb_b200 sm_100a <build tag>" */
+BNB_B200_API const char *cbnb_version(void);
+/* device self-test: number of fp32 bit patterns (all 2^32 are tried) for which the shared-memory-LUT
+ * 4-bit quantiser disagrees with the reference decision tree; qtype 1 = FP4, 2 = NF4. Must return 0. */
+BNB_B200_API long long cbnb_selftest_quant_lut(int qtype);
+
+/* GEMV with the NESTED (double-quantised) absmax consumed directly: qabsmax uint8 [N*K/blocksize],
+ * absmax2 fp32 [ceil(nblocks/blocksize2)], code2 fp32[256], offset scalar. De-nesting is
+ * fl(fl(code2[q] * absmax2[i / blocksize2]) + offset), identical to functional.py:1982-1984. */
+BNB_B200_API void cgemm_4bit_inference_nested_fp16(int m, int n, int k, void *A, unsigned char *B, unsigned char *qabsmax, float *absmax2, float *code2, float offset, float *datatype, void *out, int lda, int ldb, int ldc, int blocksize, int blocksize2);
+BNB_B200_API void cgemm_4bit_inference_nested_bf16(int m, int n, int k, void *A, unsigned char *B, unsigned char *qabsmax, float *absmax2, float *code2, float offset, float *datatype, void *out, int lda, int ldb, int ldc, int blocksize, int blocksize2);
+
+/* batch > 1 fused 4-bit GEMM (replaces dequantize_4bit + F.linear, autograd/_functions.py:490-518):
+ * out[b, j] = sum_k A[b,k] * T(code[q(j,k)] * absmax[(j*K+k)/blocksize]) (+ bias[j]); A: [batch, K] T row-major,
+ * B packed [N, K/2], out [batch, N] T. tcgen05 kind::f16, TMEM fp32 accumulators. */
+BNB_B200_API int cgemm_4bit_fp16(int batch, int N, int K, void *A, unsigned char *B, float *absmax, float *datatype, void *bias, void *out, int blocksize);
+BNB_B200_API int cgemm_4bit_bf16(int batch, int N, int K, void *A, unsigned char *B, float *absmax, float *datatype, void *bias, void *out, int blocksize);
+
+/* B200-native int8 GEMM on ROW-MAJOR operands (the layout tcgen05 + TMA consume directly):
+ * C[i,j] = sum_k A[i,k] * B[j,k]; A [m,k], B [n,k] int8 row-major (K-major), C int32 row-major [m,n]. */
+BNB_B200_API int cigemm_rowmajor_32(int m, int n, int k, const int8_t *A, const int8_t *B, int *C);
+/* same GEMM with the mm_dequant epilogue fused: out fp16 row-major [m,n] =
+ * half(((float(acc) * 6.200012e-05f) * rowStats[i]) * colStats[j] + bias[j]) */
+BNB_B200_API int cigemm_rowmajor_dequant_fp16(int m, int n, int k, const int8_t *A, const int8_t *B, float *rowStats, float *colStats, void *bias, void *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNB_B200_H */

@@ -1,0 +1,123 @@
+"""CPU-only checks of the drop-in boundary: the library loads, exports every symbol include/bnb_b200.h
+declares (no compute calls), and the host-side mirror matches the golden fixtures."""
+import ctypes as ct
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "bnb_b200.h")).read()
+    return re.findall(r"BNB_B200_API\s+[\w\s\*]+?\b(\w+)\s*\(", src)
+
+
+def test_header_declares_the_reference_hot_path_abi():
+    syms = set(declared_symbols())
+    # the 41 hot-path symbols of SURVEY.md section 8b (minus the two CPU-only ones, which need no GPU library)
+    want = set()
+    for t in ("fp32", "fp16", "bf16"):
+        for q in ("", "_fp4", "_nf4"):
+            want.add(f"cquantize_blockwise_{t}{q}")
+            want.add(f"cdequantize_blockwise_{t}{q}")
+        want.add(f"cgemm_4bit_inference_naive_{t}")
+    want |= {"cget_col_row_stats", "cdouble_rowcol_quant", "cdequant_mm_int32_fp16", "get_context",
+             "cextractOutliers_turing", "cextractOutliers_ampere"}
+    for f in ("col32", "turing", "ampere"):
+        want |= {f"ctransform_row2{f}", f"ctransform_row2{f}T"}
+    for f in ("turing", "ampere"):
+        want |= {f"cigemmlt_{f}_32", f"cigemmlt_{f}_8", f"cigemmlt_{f}_8_rowscale"}
+    assert len(want) == 39
+    assert want <= syms, sorted(want - syms)
+
+
+def test_library_exports_every_declared_symbol():
+    from bnb_b200.cextension import LIB_PATH, lib
+    assert os.path.exists(LIB_PATH)
+    dll = ct.CDLL(LIB_PATH)
+    missing = [s for s in declared_symbols() if not hasattr(dll, s)]
+    assert not missing, missing
+    assert lib.cbnb_version().startswith(b"bnb_b200 sm_100a")
+
+
+def test_library_is_sm100a_tensor_path():
+    """cuobjdump (when present) must show tcgen05 / TMA SASS in the shipped library."""
+    import shutil
+    import subprocess
+    from bnb_b200.cextension import LIB_PATH
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([exe, "-sass", LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCIMMA", "UTMALDG", "LDTM", "HMMA"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_stream_setter_roundtrip_without_gpu():
+    from bnb_b200.cextension import lib
+    lib.cbnb_set_stream(ct.c_void_p(0x1234))
+    assert lib.cbnb_get_stream() == 0x1234
+    lib.cbnb_set_stream(None)
+    assert lib.cbnb_get_stream() in (None, 0)
+    assert lib.cbnb_last_error() == 0
+
+
+def test_python_codebooks_match_reference_golden():
+    from bnb_b200 import functional as F
+    g = np.load(os.path.join(GOLDEN, "ref_python_tables.npz"))
+    assert np.array_equal(F.create_dynamic_map().numpy(), g["dynamic_map"])
+    assert np.array_equal(F.get_4bit_type("nf4", device="cpu").numpy(), g["nf4"])
+    assert np.array_equal(F.get_4bit_type("fp4", device="cpu").numpy(), g["fp4"])
+
+
+def test_kernel_constants_match_reference_source():
+    """The literals in csrc/codebooks.cuh are the literals of the reference kernel source."""
+    consts = json.load(open(os.path.join(GOLDEN, "ref_kernel_constants.json")))
+    src = open(os.path.join(ROOT, "bitsandbytes-sycl_b200", "csrc", "codebooks.cuh")).read()
+
+    def macro(name):
+        m = re.search(r"#define " + name + r"\s*\\?\s*\{(.*?)\}", src, re.S)
+        return [x.strip().rstrip("f") for x in m.group(1).replace("\\", "").split(",") if x.strip()]
+
+    assert [float(x) for x in macro("BNB_NF4_TABLE")] == [float(x) for x in consts["nf4_table"]]
+    assert macro("BNB_NF4_THRESHOLDS") == consts["nf4_thresholds_ascending"]
+    assert sorted(macro("BNB_FP4_THRESHOLDS"), key=float) == sorted(consts["fp4_quant_thresholds_tree_order"], key=float)
+    assert [float(x) for x in macro("BNB_FP4_MAGNITUDES")] == [float(x) for x in consts["fp4_dequant_by_low3bits"]]
+    int8_src = open(os.path.join(ROOT, "bitsandbytes-sycl_b200", "csrc", "int8_quant.cu")).read()
+    assert consts["mm_dequant_const"] + "f" in int8_src
+
+
+def test_quantstate_dict_roundtrip_cpu():
+    from bnb_b200.functional import QuantState
+    s2 = QuantState(absmax=torch.rand(4), blocksize=256, code=torch.rand(256), dtype=torch.float32)
+    qs = QuantState(absmax=torch.randint(0, 255, (1024,), dtype=torch.uint8), shape=torch.Size([256, 256]),
+                    code=torch.rand(16), blocksize=64, quant_type="nf4", dtype=torch.bfloat16,
+                    offset=torch.tensor(0.25), state2=s2)
+    packed = qs.as_dict(packed=True)
+    assert "quant_state.bitsandbytes__nf4" in packed and all(isinstance(v, torch.Tensor) for v in packed.values())
+    back = QuantState.from_dict(dict(packed), device=torch.device("cpu"))
+    assert back == qs and back.nested and back.state2.blocksize == 256 and back.dtype == torch.bfloat16
+
+
+def test_no_cpu_fallback():
+    from bnb_b200 import functional as F
+    with pytest.raises(NotImplementedError):
+        F.quantize_4bit(torch.randn(64), quant_type="nf4")
+    with pytest.raises(NotImplementedError):
+        F.quantize_blockwise(torch.randn(4096))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "bitsandbytes-sycl_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(d, f)).read()
+                assert "oracle" not in txt.replace("# oracle", ""), os.path.join(d, f)

@@ -1,0 +1,137 @@
+"""GPU parity: 4-bit GEMV (K3) through the C-ABI vs the oracle.
+Floating point -> tolerance gates, stated here (derived from the three rounding chains):
+  bf16:  rel-L2 <= 2.5e-3 vs the fp64-exact product, and <= 5e-3 vs the reference-faithful T-arithmetic chain
+  fp16:  rel-L2 <= 6e-4 vs exact;   fp32: rel-L2 <= 2e-6 vs exact
+and the kernel must be no less accurate than the reference chain (w.r.t. exact)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import DT, bits_equal, from_bits, rel_l2, to_bits
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL_EXACT = {"bf16": 2.5e-3, "fp16": 6e-4, "fp32": 2e-6}
+TOL_FAITHFUL = {"bf16": 5e-3, "fp16": 1.5e-3, "fp32": 2e-6}
+
+
+@pytest.fixture(scope="module")
+def F():
+    assert torch.cuda.is_available()
+    from bnb_b200 import functional
+    return functional
+
+
+def make_case(F, N, K, dtype, qtype="nf4", nested=True, blocksize=64, seed=0):
+    torch.manual_seed(seed)
+    W = (torch.randn(N, K) * 0.02).to(DT[dtype])
+    x = torch.randn(1, K).to(DT[dtype])
+    q, st = F.quantize_4bit(W.cuda(), blocksize=blocksize, compress_statistics=nested, quant_type=qtype)
+    return W, x, q, st
+
+
+def oracle_outputs(F, x, q, st, N, K, dtype):
+    qn = q.cpu().numpy().ravel()
+    if st.nested:
+        absmax = orc.denest_absmax(st.absmax.cpu().numpy(), st.state2.absmax.cpu().numpy(),
+                                   st.state2.code.cpu().numpy(), np.float32(st.offset.item()), st.state2.blocksize)
+    else:
+        absmax = st.absmax.cpu().numpy()
+    code = st.code.cpu().numpy()
+    xb = to_bits(x).ravel()
+    exact = orc.gemm_4bit_exact(xb, dtype, qn, absmax, code, 1, N, K, st.blocksize)[0]
+    faithful = orc.gemv_4bit(xb, dtype, qn, absmax, code, N, K, st.blocksize, 0)
+    faithful = from_bits(faithful, dtype).double().numpy()
+    return exact, faithful
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16", "fp32"])
+@pytest.mark.parametrize("shape", [(4096, 4096), (11008, 4096), (4096, 11008)])
+def test_gemv_config2_shapes(F, dtype, shape):
+    """BASELINE config 2: Llama-2-7B shapes, NF4, blocksize 64, double-quantised absmax, batch 1."""
+    N, K = shape
+    W, x, q, st = make_case(F, N, K, dtype)
+    y = F.gemv_4bit(x.cuda(), q.t(), state=st)
+    assert y.shape == (1, N) and y.dtype == DT[dtype]
+    exact, faithful = oracle_outputs(F, x, q, st, N, K, dtype)
+    yk = y.double().cpu().numpy().ravel()
+    err_exact = rel_l2(yk, exact)
+    err_ref_chain = rel_l2(faithful, exact)
+    assert err_exact <= TOL_EXACT[dtype], (err_exact,)
+    assert rel_l2(yk, faithful) <= TOL_FAITHFUL[dtype]
+    assert err_exact <= err_ref_chain * 1.05 + 1e-7, (err_exact, err_ref_chain)   # no less accurate than the reference
+    rms = np.sqrt(np.mean(exact ** 2))
+    ulp = {"bf16": 2.0 ** -7, "fp16": 2.0 ** -10, "fp32": 2.0 ** -20}[dtype]
+    assert np.all(np.abs(yk - exact) <= ulp * np.abs(exact) + ulp / 2 * rms)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+def test_fused_nested_equals_denested_path(F, dtype):
+    """One-launch nested GEMV == de-nest (2 launches) + GEMV: same arithmetic, bit-identical outputs."""
+    N, K = 1024, 2048
+    W, x, q, st = make_case(F, N, K, dtype, seed=3)
+    y_fused = F.gemv_4bit(x.cuda(), q.t(), state=st)
+    old = F.FUSED_NESTED_GEMV
+    try:
+        F.FUSED_NESTED_GEMV = False
+        y_ref_path = F.gemv_4bit(x.cuda(), q.t(), state=st)
+    finally:
+        F.FUSED_NESTED_GEMV = old
+    assert torch.equal(y_fused.view(torch.int16), y_ref_path.view(torch.int16))
+
+
+@pytest.mark.parametrize("qtype", ["nf4", "fp4"])
+@pytest.mark.parametrize("blocksize", [64, 128, 512])
+@pytest.mark.parametrize("nested", [False, True])
+def test_gemv_variants(F, qtype, blocksize, nested):
+    N, K = 520, 1536                               # N not a multiple of 16, K = 24 * 64
+    W, x, q, st = make_case(F, N, K, "bf16", qtype, nested, blocksize, seed=7)
+    y = F.gemv_4bit(x.cuda(), q.t(), state=st)
+    exact, faithful = oracle_outputs(F, x, q, st, N, K, "bf16")
+    assert rel_l2(y.double().cpu().numpy(), exact) <= TOL_EXACT["bf16"]
+
+
+def test_gemv_3d_input_and_module_dispatch(F):
+    from bnb_b200.nn import LinearNF4
+    torch.manual_seed(11)
+    lin = LinearNF4(1024, 768, bias=True, compute_dtype=torch.bfloat16)
+    ref_w = lin.weight.data.clone()
+    ref_b = lin.bias.data.clone()
+    lin = lin.cuda()
+    assert lin.weight.dtype == torch.uint8 and lin.weight.quant_state.nested
+    x = torch.randn(1, 1, 1024, dtype=torch.bfloat16, device="cuda")
+    y = lin(x)                                       # batch 1 -> gemv path
+    assert y.shape == (1, 1, 768)
+    Wd = F.dequantize_4bit(lin.weight.data, lin.weight.quant_state).float()
+    y_ref = x.float().reshape(1, -1) @ Wd.t() + ref_b.cuda().float()
+    assert rel_l2(y.float().cpu().numpy(), y_ref.cpu().numpy()) < 5e-3
+    xb = torch.randn(4, 7, 1024, dtype=torch.bfloat16, device="cuda")
+    yb = lin(xb)                                     # batch > 1 -> MatMul4Bit
+    yb_ref = xb.float() @ Wd.t() + ref_b.cuda().float()
+    assert yb.shape == (4, 7, 768)
+    assert rel_l2(yb.float().cpu().numpy(), yb_ref.cpu().numpy()) < 5e-3
+    # the reference's own test bar (tests_pvc/autograd.py:389-391): mean |out_bnb - out_torch| < 0.115
+    y_fp = xb.float() @ ref_w.cuda().float().t() + ref_b.cuda().float()
+    assert (yb.float() - y_fp).abs().mean().item() < 0.115
+
+
+def test_gemv_generic_path_odd_shapes(F):
+    """K not a multiple of 64 / fp32: the generic CUDA path; tail semantics of kernel_gemm.cpp:1312-1366."""
+    import ctypes as ct
+    torch.manual_seed(2)
+    N, K, bs = 37, 96, 32
+    W = torch.randn(N, K) * 0.05
+    x = torch.randn(K)
+    q_ref, am_ref = orc.quantize_blockwise(W.numpy().ravel(), "fp32", None, bs, "nf4")
+    code = orc.nf4_table()
+    out = torch.zeros(N, device="cuda")
+    qd, amd, cd, xd = (torch.from_numpy(a).cuda() for a in (q_ref, am_ref, code, x.numpy()))
+    F.lib.cbnb_set_stream(ct.c_void_p(torch.cuda.current_stream().cuda_stream))
+    F.lib.cgemm_4bit_inference_naive_fp32(ct.c_int(N), ct.c_int(1), ct.c_int(K), ct.c_void_p(xd.data_ptr()),
+                                          ct.c_void_p(qd.data_ptr()), ct.c_void_p(amd.data_ptr()),
+                                          ct.c_void_p(cd.data_ptr()), ct.c_void_p(out.data_ptr()), ct.c_int(N),
+                                          ct.c_int(K // 2), ct.c_int(N), ct.c_int(bs))
+    torch.cuda.synchronize()
+    assert F.lib.cbnb_last_error() == 0
+    exact = orc.gemm_4bit_exact(x.numpy(), "fp32", q_ref, am_ref, code, 1, N, K, bs)[0]
+    assert rel_l2(out.cpu().numpy(), exact) < 2e-6

@@ -1,0 +1,227 @@
+"""GPU parity: the LLM.int8 path (K5-K7) through the C-ABI vs the oracle.
+Bar: row/col stats, nnz counts, int8 codes, COO entries, layouts and int32 accumulators are bit-exact;
+mm_dequant (fixed fp32 op order) is bit-exact as well."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import bits_equal, rel_l2, to_bits
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def F():
+    assert torch.cuda.is_available()
+    from bnb_b200 import functional
+    return functional
+
+
+def make_acts(rows, cols, seed=0, outliers=True):
+    torch.manual_seed(seed)
+    A = torch.randn(rows, cols).half()
+    if outliers:
+        g = torch.Generator().manual_seed(seed + 1)
+        for c in torch.randint(0, cols, (6,), generator=g).tolist():
+            A[:, c] = 8.0 * torch.sign(torch.randn(rows, generator=g)).half()   # tests_pvc/test_matmulqlt.py:291-292 style
+        A[rows // 2, cols // 3] = 6.0                                            # exactly the threshold
+        A[0, 0] = -7.25
+    return A
+
+
+@pytest.mark.parametrize("shape", [(64, 256), (37, 300), (130, 1000), (512, 4096), (1, 8)])
+@pytest.mark.parametrize("threshold", [0.0, 6.0])
+def test_stats_and_double_quant_bit_exact(F, shape, threshold):
+    rows, cols = shape
+    A = make_acts(rows, cols, seed=rows, outliers=threshold > 0)
+    An = A.numpy()
+    rs, cs, nnz = F.get_colrow_absmax(A.cuda(), threshold=threshold)
+    rs_ref, cs_ref, nnz_ref = orc.get_col_row_stats(An, threshold)
+    assert np.array_equal(rs.cpu().numpy().view(np.uint32), rs_ref.view(np.uint32))
+    assert np.array_equal(cs.cpu().numpy().view(np.uint32), cs_ref.view(np.uint32))
+    if threshold > 0:
+        assert np.array_equal(nnz.cpu().numpy(), np.cumsum(nnz_ref).astype(np.int32))
+    else:
+        assert nnz is None
+    out_row, out_col, rs2, cs2, coo = F.double_quant(A.cuda(), threshold=threshold)
+    ptr = None if nnz_ref is None else np.cumsum(nnz_ref).astype(np.int32)
+    r_ref, c_ref, ri, ci, val = orc.double_rowcol_quant(An, rs_ref, cs_ref, ptr, threshold)
+    assert np.array_equal(out_row.cpu().numpy(), r_ref)
+    assert np.array_equal(out_col.cpu().numpy(), c_ref)
+    if threshold > 0 and ri is not None and ri.size:
+        assert coo is not None and coo.nnz == ri.size
+        got = sorted(zip(coo.rowidx.cpu().tolist(), coo.colidx.cpu().tolist(),
+                         coo.values.cpu().view(torch.int16).tolist()))
+        want = sorted(zip(ri.tolist(), ci.tolist(), val.view(np.int16).tolist()))
+        assert got == want                                   # as a set (reference order is atomic-arbitrary)
+        assert torch.all(coo.rowidx[1:] >= coo.rowidx[:-1])  # sorted by row, like the reference's post-sort
+        # outlier positions are 0 in the row-quantised matrix
+        assert torch.all(out_row[coo.rowidx.long(), coo.colidx.long()] == 0)
+    else:
+        assert coo is None
+
+
+def test_double_quant_zero_row_and_column(F):
+    A = make_acts(32, 256, outliers=False)
+    A[5, :] = 0
+    A[:, 17] = 0
+    out_row, out_col, rs, cs, _ = F.double_quant(A.cuda())
+    assert rs[5].item() == 0.0 and cs[17].item() == 0.0
+    assert torch.all(out_row[5] == 0) and torch.all(out_col[:, 17] == 0)     # 0 * inf = NaN -> 0 (defined)
+
+
+@pytest.mark.parametrize("fmt", ["col32", "col_turing", "col_ampere"])
+@pytest.mark.parametrize("shape", [(32, 32), (7, 33), (40, 100), (129, 65), (256, 512)])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_transforms_bit_exact(F, fmt, shape, transpose):
+    rng = np.random.RandomState(shape[0])
+    A = rng.randint(-128, 128, shape).astype(np.int8)
+    out, S = F.transform(torch.from_numpy(A).cuda(), fmt, transpose=transpose)
+    ref = orc.transform(A, fmt, transpose)
+    assert out.numel() == ref.size
+    assert np.array_equal(out.cpu().numpy().ravel(), ref)
+    assert S[1] == fmt
+
+
+@pytest.mark.parametrize("fmtB", ["col_turing", "col_ampere"])
+@pytest.mark.parametrize("mnk", [(32, 32, 32), (19, 45, 96), (128, 256, 128), (200, 300, 528), (16, 40, 72)])
+def test_igemmlt_reference_layouts_exact(F, fmtB, mnk):
+    """cigemmlt_<fmt>_32 with the reference's operand layouts: exact int32, col32 output."""
+    m, n, k = mnk
+    rng = np.random.RandomState(m + n)
+    A = rng.randint(-128, 128, (m, k)).astype(np.int8)
+    B = rng.randint(-128, 128, (n, k)).astype(np.int8)
+    C32A, SA = F.transform(torch.from_numpy(A).cuda(), "col32")
+    CxB, SB = F.transform(torch.from_numpy(B).cuda(), fmtB)
+    out, Sout = F.igemmlt(C32A, CxB, SA, SB)
+    assert Sout[1] == "col32" and out.dtype == torch.int32
+    ref = orc.igemmlt_32(orc.transform(A, "col32"), orc.transform(B, fmtB), m, n, k, fmtB)
+    assert np.array_equal(out.cpu().numpy().ravel(), ref)
+    idx = np.unique(rng.randint(0, k, 5)).astype(np.int32)
+    got = F.extract_outliers(CxB, SB, torch.from_numpy(idx).cuda())
+    assert np.array_equal(got.cpu().numpy(), B[:, idx])
+
+
+@pytest.mark.parametrize("mnk", [(128, 256, 128), (1, 8, 16), (130, 260, 144), (384, 512, 1024), (1000, 1000, 1008),
+                                 (64, 64, 40)])
+def test_igemm_rowmajor_exact(F, mnk):
+    """B200-native row-major tcgen05 kind::i8 GEMM (and the SIMT path for K % 16 != 0): exact int32."""
+    m, n, k = mnk
+    rng = np.random.RandomState(k)
+    A = rng.randint(-128, 128, (m, k)).astype(np.int8)
+    B = rng.randint(-128, 128, (n, k)).astype(np.int8)
+    out, _ = F.igemmlt(torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), ((m, k), "row"), ((n, k), "row"))
+    ref = A.astype(np.int32) @ B.astype(np.int32).T
+    assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def test_igemm_extreme_values_exact(F):
+    """all -128 * -128 over K = 4096: 2^26 per output, far from overflow; +-127 / -128 mixes."""
+    m, n, k = 128, 256, 4096
+    A = np.full((m, k), -128, np.int8)
+    B = np.full((n, k), -128, np.int8)
+    B[1::2] = 127
+    out, _ = F.igemmlt(torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), ((m, k), "row"), ((n, k), "row"))
+    ref = A.astype(np.int64) @ B.astype(np.int64).T
+    assert np.array_equal(out.cpu().numpy().astype(np.int64), ref)
+
+
+@pytest.mark.parametrize("shape", [(128, 256), (77, 100), (256, 1024)])
+@pytest.mark.parametrize("bias", [False, True])
+def test_mm_dequant_bit_exact(F, shape, bias):
+    rows, cols = shape
+    rng = np.random.RandomState(rows)
+    C = rng.randint(-2 ** 22, 2 ** 22, (rows, cols)).astype(np.int32)
+    rs = np.abs(rng.randn(rows)).astype(np.float32) * 3
+    cs = np.abs(rng.randn(cols)).astype(np.float32)
+    b = (rng.randn(cols)).astype(np.float16) if bias else None
+    C32 = orc.transform(C, "col32")
+    out = F.mm_dequant(torch.from_numpy(C32).cuda(), ((rows, cols), "col32"), torch.from_numpy(rs).cuda(),
+                       torch.from_numpy(cs).cuda(), bias=None if b is None else torch.from_numpy(b).cuda())
+    ref = orc.mm_dequant(C32, rs, cs, rows, cols, b, col32=True)
+    assert bits_equal(out, ref.view(np.uint16))
+
+
+@pytest.mark.parametrize("mnk", [(256, 512, 256), (130, 264, 144)])
+def test_fused_igemm_dequant_bit_exact(F, mnk):
+    """cigemm_rowmajor_dequant_fp16 == igemm (exact) -> mm_dequant (oracle), bit for bit."""
+    m, n, k = mnk
+    rng = np.random.RandomState(7)
+    A = rng.randint(-127, 128, (m, k)).astype(np.int8)
+    B = rng.randint(-127, 128, (n, k)).astype(np.int8)
+    rs = (np.abs(rng.randn(m)) + 0.5).astype(np.float32)
+    cs = (np.abs(rng.randn(n)) + 0.5).astype(np.float32)
+    b = rng.randn(n).astype(np.float16)
+    out = F.int8_linear_dequant(torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), torch.from_numpy(rs).cuda(),
+                                torch.from_numpy(cs).cuda(), bias=torch.from_numpy(b).cuda())
+    C = A.astype(np.int32) @ B.astype(np.int32).T
+    ref = orc.mm_dequant(C, rs, cs, m, n, b, col32=False)
+    assert bits_equal(out, ref.view(np.uint16))
+
+
+@pytest.mark.parametrize("threshold", [0.0, 6.0])
+@pytest.mark.parametrize("has_bias", [False, True])
+def test_linear8bitlt_forward(F, threshold, has_bias):
+    """Module-level check in the style of the reference's tests (tests_pvc/autograd.py:216-324,
+    tolerances :277-280): <= 1.75 % of elements outside atol 0.01 / rtol 0.1 vs the fp16 torch result."""
+    from bnb_b200.nn import Linear8bitLt
+    torch.manual_seed(3)
+    lin = Linear8bitLt(1024, 768, bias=has_bias, has_fp16_weights=False, threshold=threshold)
+    torch.nn.init.xavier_uniform_(lin.weight)
+    W = lin.weight.data.clone().half()
+    b = lin.bias.data.clone().half() if has_bias else None
+    lin = lin.cuda().half()
+    assert lin.weight.dtype == torch.int8
+    A = torch.randn(96, 1024, dtype=torch.float16, device="cuda")
+    if threshold > 0:
+        A[:, [5, 100, 777]] = 6.0                      # autograd.py:228-230
+    out = lin(A)
+    ref = torch.nn.functional.linear(A, W.cuda(), None if b is None else b.cuda())
+    assert out.shape == ref.shape and out.dtype == torch.float16
+    close = torch.isclose(out, ref, atol=0.01, rtol=0.1)
+    assert (close == 0).sum().item() <= out.numel() * 0.0175
+    close2 = torch.isclose(out, ref, atol=0.035, rtol=0.2)
+    assert (close2 == 0).sum().item() <= out.numel() * 0.001
+    out2 = lin(A)                                      # second call reuses the state
+    assert torch.equal(out, out2)
+
+
+def test_linear8bitlt_matches_reference_layout_path(F):
+    """Native row-major fused path == the reference-shaped path (col32/col_turing transforms, igemmlt,
+    mm_dequant) bit for bit."""
+    from bnb_b200 import matmul, MatmulLtState
+    torch.manual_seed(9)
+    W = (torch.randn(512, 1024) * 0.03).half().cuda()
+    A = torch.randn(64, 1024, dtype=torch.float16, device="cuda")
+    A[:, 3] = 7.0
+    bias = torch.randn(512, dtype=torch.float16, device="cuda")
+    outs = []
+    for fmt in ("row", "col_turing", "col_ampere"):
+        st = MatmulLtState()
+        st.formatB = fmt
+        st.threshold = 6.0
+        st.has_fp16_weights = False
+        CB, _, SCB, _, _ = F.double_quant(W)
+        st.CB, st.SCB = CB, SCB
+        outs.append(matmul(A, CB, state=st, bias=bias))
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+def test_config3_full_size_checksum(F):
+    """BASELINE config 3 at full size: 4096 tokens x 4096 -> 16384, exact int32.  Size-independent
+    property: sum_j C[i, j] == A[i, :] . (sum_j B[j, :]) and sum_i C[i, j] == (sum_i A[i, :]) . B[j, :]
+    in exact integer arithmetic, plus a 16-row slab against the CPU oracle."""
+    m, k, n = 4096, 4096, 16384
+    g = torch.Generator(device="cuda").manual_seed(0)
+    A = torch.randint(-127, 128, (m, k), dtype=torch.int8, device="cuda", generator=g)
+    B = torch.randint(-127, 128, (n, k), dtype=torch.int8, device="cuda", generator=g)
+    C, _ = F.igemmlt(A, B, ((m, k), "row"), ((n, k), "row"))
+    row_sum = C.sum(dim=1, dtype=torch.int64)
+    col_sum = C.sum(dim=0, dtype=torch.int64)
+    Bs = B.sum(dim=0, dtype=torch.int64).double()          # |.| <= 127*16384 < 2^21, products sum < 2^45: exact in fp64
+    As = A.sum(dim=0, dtype=torch.int64).double()
+    assert torch.equal(row_sum, (A.double() @ Bs).long())
+    assert torch.equal(col_sum, (B.double() @ As).long())
+    slab = orc.igemm_rowmajor(A[1000:1016].cpu().numpy(), B[5000:5128].cpu().numpy())
+    assert np.array_equal(C[1000:1016, 5000:5128].cpu().numpy(), slab)
