@@ -74,10 +74,18 @@ _NF4 = [-1.0, -0.6961928009986877, -0.5250730514526367, -0.39491748809814453, -0
 _FP4 = [0, 0.0625, 8.0, 12.0, 4.0, 6.0, 2.0, 3.0, -0, -0.0625, -8.0, -12.0, -4.0, -6.0, -2.0, -3.0]
 
 
+_code_cache: Dict[Tuple[str, str], Tensor] = {}
+
+
 def get_4bit_type(typename, device=None, blocksize=64):
-    """16-entry code of a 4-bit type, normalised to absmax 1 (reference :1020-1099)."""
+    """16-entry code of a 4-bit type, normalised to absmax 1 (reference :1020-1099).  The device tensor is
+    built once per (type, device) and shared (read-only) -- no host->device copy per quantize call."""
     if device is None:
         device = "cuda"
+    key = (typename, str(torch.device(device)) if not isinstance(device, torch.device) else str(device))
+    cached = _code_cache.get(key)
+    if cached is not None:
+        return cached
     if typename == "nf4":
         data = _NF4
     elif typename == "fp4":
@@ -89,6 +97,7 @@ def get_4bit_type(typename, device=None, blocksize=64):
     data = torch.tensor(data, dtype=torch.float32, device=device)
     data.div_(data.abs().max())
     assert data.numel() == 16
+    _code_cache[key] = data
     return data
 
 

@@ -17,6 +17,8 @@
 //   * a CTA owns 16 output rows, its 8 warps split K in 256-element chunks with register
 //     double-buffering (8 x 64-bit loads per lane in flight per chunk), deterministic smem reduction.
 // The MMA's n dimension carries the batch (1..8 activations rows) at no extra cost.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace bnb {
@@ -52,6 +54,7 @@ template <> struct MmaT<__nv_bfloat16> {
 
 struct GemvArgs {
   int N, K, batch, blocksize;
+  int bs_shift, bs2_shift;   // log2(blocksize), log2(blocksize2)
   const void *x;             // [batch, K] T
   const unsigned char *B;    // [N, K/2]
   const float *absmax;       // fp32 [N*K/blocksize]            (plain)
@@ -59,7 +62,6 @@ struct GemvArgs {
   const float *absmax2;      // fp32 [ceil(nblocks/blocksize2)] (nested)
   const float *code2;        // fp32[256]                       (nested)
   float offset;
-  int blocksize2;
   const float *code;         // fp32[16]
   void *out;                 // [batch, N] T
 };
@@ -69,80 +71,90 @@ struct ChunkRegs {
   float am[4][2];  // de-nested absmax per step / row half
 };
 
-template <bool NESTED>
-__device__ __forceinline__ float load_absmax(const GemvArgs &a, long blk, const float *s_code2) {
-  if (NESTED) {
-    float v = __fmul_rn(s_code2[a.qabsmax[blk]], __ldg(a.absmax2 + blk / a.blocksize2));
-    return __fadd_rn(v, a.offset);
-  }
-  return __ldg(a.absmax + blk);
-}
-
-template <bool NESTED>
-__device__ __forceinline__ void load_chunk(ChunkRegs &r, const GemvArgs &a, int k0, long row_lo, long row_hi,
-                                           int t, const float *s_code2) {
-  const long rows[2] = {row_lo, row_hi};
+// VEC4: blocksize == 64 and K % 256 == 0 -> the four absmax entries of a 256-element chunk are one
+// aligned 32-bit (nested, uint8) or 128-bit (fp32) load and share one absmax2 entry.
+template <bool NESTED, bool VEC4>
+__device__ __forceinline__ void load_chunk(ChunkRegs &r, const GemvArgs &a, int k0, const unsigned char *const (&wrow)[2],
+                                           const long (&ebase)[2], const float *s_code2) {
 #pragma unroll
   for (int s = 0; s < 4; s++) {
     const int k = k0 + s * 64;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      if (k < a.K) {
-        r.w[s][h] = ld_stream_u2(a.B + (rows[h] * a.K + k) / 2 + t * 8);
+    for (int h = 0; h < 2; h++) r.w[s][h] = (k < a.K) ? ld_stream_u2(wrow[h] + (k >> 1)) : make_uint2(0, 0);
+  }
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    if (VEC4) {
+      const long blk = (ebase[h] + k0) >> 6;  // multiple of 4
+      if (NESTED) {
+        const uint32_t q4 = __ldg(reinterpret_cast<const uint32_t *>(a.qabsmax + blk));
+        const float am2 = __ldg(a.absmax2 + (blk >> a.bs2_shift));
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+          r.am[s][h] = __fadd_rn(__fmul_rn(s_code2[(q4 >> (8 * s)) & 0xFFu], am2), a.offset);
       } else {
-        r.w[s][h] = make_uint2(0, 0);
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(a.absmax + blk));
+        r.am[0][h] = v.x; r.am[1][h] = v.y; r.am[2][h] = v.z; r.am[3][h] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < 4; s++) {
+        const int k = k0 + s * 64;
+        float v = 0.0f;
+        if (k < a.K) {
+          const long blk = (ebase[h] + k) >> a.bs_shift;
+          if (NESTED) v = __fadd_rn(__fmul_rn(s_code2[a.qabsmax[blk]], __ldg(a.absmax2 + (blk >> a.bs2_shift))), a.offset);
+          else v = __ldg(a.absmax + blk);
+        }
+        r.am[s][h] = v;
       }
     }
   }
-#pragma unroll
-  for (int s = 0; s < 4; s++) {
-    const int k = k0 + s * 64;
-#pragma unroll
-    for (int h = 0; h < 2; h++)
-      r.am[s][h] = (k < a.K) ? load_absmax<NESTED>(a, (rows[h] * a.K + k) / a.blocksize, s_code2) : 0.0f;
-  }
 }
 
-template <typename T, bool NESTED>
+template <typename T, bool NESTED, bool VEC4>
 __global__ void __launch_bounds__(kGemvThreads) k_gemv4_mma(const GemvArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned char *s_lut = smem;                                              // 64 KB
   float *s_red = reinterpret_cast<float *>(smem + kGemvLutBytes);           // [8 warps][16][8]
-  float *s_code2 = s_red + kGemvWarps * 128;                                // [256] (nested only)
+  float *s_code2 = s_red + kGemvWarps * 128;                                // [256]
+  uint32_t *s_codeT = reinterpret_cast<uint32_t *>(s_code2 + 256);          // [16] code rounded to T (low 16 bits)
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int row0 = blockIdx.x * 16;
   const long row_lo = min(row0 + g, a.N - 1), row_hi = min(row0 + g + 8, a.N - 1);
   const int nchunks = (a.K + kChunkK - 1) / kChunkK;
+  const unsigned char *const wrow[2] = {a.B + row_lo * (a.K >> 1) + t * 8, a.B + row_hi * (a.K >> 1) + t * 8};
+  const long ebase[2] = {row_lo * a.K, row_hi * a.K};
 
-  if (NESTED) {
-    s_code2[threadIdx.x] = a.code2[threadIdx.x];  // 256 threads
-    __syncthreads();
-  }
+  if (NESTED) s_code2[threadIdx.x] = a.code2[threadIdx.x];  // 256 threads
+  if (threadIdx.x < 16) s_codeT[threadIdx.x] = MmaT<T>::pack(a.code[threadIdx.x], 0.0f) & 0xFFFFu;
+  __syncthreads();
+
   // first chunk's loads go out before the table is built so the two overlap
   ChunkRegs cur, nxt;
   int c = warp;
-  if (c < nchunks) load_chunk<NESTED>(cur, a, c * kChunkK, row_lo, row_hi, t, s_code2);
+  if (c < nchunks) load_chunk<NESTED, VEC4>(cur, a, c * kChunkK, wrow, ebase, s_code2);
 
-  {  // byte -> {T(code[hi nibble]), T(code[lo nibble])}, one copy per lane
-    const int e = threadIdx.x;
-    const uint32_t v = MmaT<T>::pack(__ldg(a.code + (e >> 4)), __ldg(a.code + (e & 15)));
-    uint4 *dst = reinterpret_cast<uint4 *>(s_lut + e * 256);
-    const uint4 v4 = make_uint4(v, v, v, v);
-#pragma unroll
-    for (int i = 0; i < 8; i++) dst[i] = v4;
+  // byte -> {T(code[hi nibble]), T(code[lo nibble])}, one copy per lane (bank == lane): each warp fills
+  // 32 entries with 128-byte conflict-free stores
+#pragma unroll 4
+  for (int i = 0; i < 32; i++) {
+    const int e = i * kGemvWarps + warp;
+    const uint32_t v = s_codeT[e >> 4] | (s_codeT[e & 15] << 16);
+    *reinterpret_cast<uint32_t *>(s_lut + e * 256 + lane * 4) = v;
   }
   __syncthreads();
 
   const uint32_t lane4 = lane * 4;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const T *xrow = reinterpret_cast<const T *>(a.x) + (long)min(g, a.batch - 1) * a.K;
+  const T *xrow = reinterpret_cast<const T *>(a.x) + (long)min(g, a.batch - 1) * a.K + t * 16;
   const bool has_x = g < a.batch;
 
   for (; c < nchunks; c += kGemvWarps) {
     const int cn = c + kGemvWarps;
-    if (cn < nchunks) load_chunk<NESTED>(nxt, a, cn * kChunkK, row_lo, row_hi, t, s_code2);
+    if (cn < nchunks) load_chunk<NESTED, VEC4>(nxt, a, cn * kChunkK, wrow, ebase, s_code2);
     const int k0 = c * kChunkK;
 #pragma unroll
     for (int s = 0; s < 4; s++) {
@@ -150,7 +162,7 @@ __global__ void __launch_bounds__(kGemvThreads) k_gemv4_mma(const GemvArgs a) {
       if (k < a.K) {
         uint4 xa = make_uint4(0, 0, 0, 0), xb = make_uint4(0, 0, 0, 0);
         if (has_x) {
-          const uint4 *xp = reinterpret_cast<const uint4 *>(xrow + k + t * 16);
+          const uint4 *xp = reinterpret_cast<const uint4 *>(xrow + k);
           xa = __ldg(xp);
           xb = __ldg(xp + 1);
         }
@@ -234,21 +246,35 @@ __global__ void __launch_bounds__(128) k_gemv4_simple(int M, int K, const T *__r
 }
 
 static bool fast_path_ok(int K, int ldb, int blocksize, const void *A, const void *B) {
-  return K > 0 && (K % 64 == 0) && ldb == K / 2 && blocksize >= 64 && (blocksize % 64 == 0) &&
+  return K > 0 && (K % 64 == 0) && ldb == K / 2 && blocksize >= 64 && ((blocksize & (blocksize - 1)) == 0) &&
          (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(B) % 8 == 0);
 }
 
-template <typename T, bool NESTED>
-static void launch_mma(const GemvArgs &a) {
-  static bool attr_set = false;
-  const size_t smem = kGemvLutBytes + kGemvWarps * 128 * sizeof(float) + (NESTED ? 256 * sizeof(float) : 0);
-  if (!attr_set) {
-    latch_error(cudaFuncSetAttribute(k_gemv4_mma<T, NESTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+static int ilog2(int v) { int s = 0; while ((1 << s) < v) s++; return s; }
+
+template <typename T, bool NESTED, bool VEC4>
+static void launch_mma_inst(const GemvArgs &a) {
+  static bool attr_set[64] = {false};
+  const size_t smem = kGemvLutBytes + kGemvWarps * 128 * sizeof(float) + 256 * sizeof(float) + 16 * sizeof(uint32_t);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_set[dev]) {
+    latch_error(cudaFuncSetAttribute(k_gemv4_mma<T, NESTED, VEC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                 "gemv smem attr");
-    attr_set = true;
+    attr_set[dev] = true;
   }
-  k_gemv4_mma<T, NESTED><<<ceil_div(a.N, 16), kGemvThreads, smem, current_stream()>>>(a);
+  k_gemv4_mma<T, NESTED, VEC4><<<ceil_div(a.N, 16), kGemvThreads, smem, current_stream()>>>(a);
   check_launch("gemv_4bit (mma)");
+}
+
+template <typename T, bool NESTED>
+static void launch_mma(GemvArgs a, int blocksize2) {
+  a.bs_shift = ilog2(a.blocksize);
+  a.bs2_shift = ilog2(blocksize2 > 0 ? blocksize2 : 1);
+  const bool vec4 = a.blocksize == 64 && (a.K % 256 == 0) &&
+                    (NESTED ? (reinterpret_cast<uintptr_t>(a.qabsmax) % 4 == 0) : (reinterpret_cast<uintptr_t>(a.absmax) % 16 == 0));
+  if (vec4) launch_mma_inst<T, NESTED, true>(a);
+  else launch_mma_inst<T, NESTED, false>(a);
 }
 
 template <typename T>
@@ -262,8 +288,8 @@ void gemv_4bit(int m, int n, int k, const T *A, const unsigned char *B, const fl
     a.N = m; a.K = k; a.batch = 1; a.blocksize = blocksize;
     a.x = A; a.B = B; a.absmax = absmax; a.code = datatype; a.out = out;
     if (sizeof(T) == 2) {
-      if (std::is_same<T, __half>::value) launch_mma<__half, false>(a);
-      else launch_mma<__nv_bfloat16, false>(a);
+      if (std::is_same<T, __half>::value) launch_mma<__half, false>(a, 0);
+      else launch_mma<__nv_bfloat16, false>(a, 0);
     }
     return;
   }
@@ -277,15 +303,15 @@ void gemv_4bit_nested(int m, int n, int k, const T *A, const unsigned char *B, c
                       int lda, int ldb, int ldc, int blocksize, int blocksize2) {
   (void)lda; (void)ldc;
   if (m <= 0 || k <= 0) return;
-  if (n < 1 || n > 8 || blocksize2 <= 0 || !fast_path_ok(k, ldb, blocksize, A, B)) {
+  if (n < 1 || n > 8 || blocksize2 <= 0 || (blocksize2 & (blocksize2 - 1)) != 0 || !fast_path_ok(k, ldb, blocksize, A, B)) {
     latch_error(cudaErrorInvalidValue, "gemv_4bit_nested: needs 1<=n<=8, K%64==0, ldb==K/2, blocksize%64==0, aligned A/B");
     return;
   }
   GemvArgs a{};
   a.N = m; a.K = k; a.batch = n; a.blocksize = blocksize;
   a.x = A; a.B = B; a.qabsmax = qabsmax; a.absmax2 = absmax2; a.code2 = code2; a.offset = offset;
-  a.blocksize2 = blocksize2; a.code = datatype; a.out = out;
-  launch_mma<T, true>(a);
+  a.code = datatype; a.out = out;
+  launch_mma<T, true>(a, blocksize2);
 }
 
 template void gemv_4bit<float>(int, int, int, const float *, const unsigned char *, const float *, const float *, float *, int, int, int, int);

@@ -14,6 +14,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <mutex>
 
 #include "codebooks.cuh"
@@ -22,43 +23,43 @@
 namespace bnb {
 
 // ------------------------------------------------------------------------------------------------
-// 4-bit quantize LUT
+// 4-bit quantize: two tiny shared-memory tables instead of a 15-compare tree
+//   base4[cell] (uint8, 129 cells of width 1/64 over [-1,1]; cell = RNE(x*64 + 64), formed with ONE fma
+//                against the 1.5*2^23 magic constant) = 4 * (number of thresholds below the cell);
+//   thr[b]      (fp32, 16 entries -> one per bank, conflict-free) = threshold between bucket b and b+1.
+// A cell holds at most one threshold, so bucket(x) = b + (x > thr[b]).  NaN and anything <= -1 are
+// mapped to -1.0 by one fmaxf (bucket 0, exactly what the all-compares-false tree returns).
 // ------------------------------------------------------------------------------------------------
-struct __align__(16) QCell {
-  float thr;
-  uint32_t lo;
-  uint32_t hi;
-  uint32_t pad;
+struct QTables {
+  unsigned char base4[256];  // byte offset into thr[] (= 4 * bucket)
+  float thr[16];             // thr[15] = +inf
+  unsigned char code[16];    // bucket -> 4-bit code (identity for NF4, {0,1,6,7,4,5,2,3} for FP4)
+  unsigned char pad[48];
 };
-constexpr int kQCells = 256;
-__device__ QCell g_qlut[2][kQCells];        // [0] = FP4 (indexed by |x|), [1] = NF4
+__device__ QTables g_qtab[2];               // [0] = FP4 (indexed by |x|), [1] = NF4
 __device__ float g_dq4_table[2][16];        // [0] = FP4, [1] = NF4 dequant values
-static QCell h_qlut[2][kQCells];
+static QTables h_qtab[2];
 static float h_dq4[2][16];
 static std::once_flag h_lut_once;
 static bool g_lut_ready[64] = {false};
 static std::mutex g_lut_mutex;
 
-// cell c holds floats x with RNE(x*1024 + 1024) in [16c, 16c+15]; built with a one-unit safety margin
-static void build_cells(QCell *cells, const float *thr, int nthr, const int *bucket_codes) {
-  for (int c = 0; c < kQCells; c++) {
-    double lo_x = (16.0 * c - 1.0 - 1024.0) / 1024.0;
-    double hi_x = (16.0 * c + 16.0 - 1024.0) / 1024.0;
-    int nbelow = 0, inside = -1, ninside = 0;
+static void build_qtables(QTables &q, const float *thr, int nthr, const int *bucket_codes) {
+  memset(&q, 0, sizeof(q));
+  for (int c = 0; c < 256; c++) {
+    // floats with RNE(x*64+64) == c lie in [(c-0.5-64)/64, (c+0.5-64)/64]; widen by a safety margin
+    const double lo_x = (c - 0.5 - 64.0) / 64.0 - 1e-6, hi_x = (c + 0.5 - 64.0) / 64.0 + 1e-6;
+    int nbelow = 0, ninside = 0;
     for (int j = 0; j < nthr; j++) {
       if ((double)thr[j] < lo_x) nbelow++;
-      else if ((double)thr[j] <= hi_x) { inside = j; ninside++; }
+      else if ((double)thr[j] <= hi_x) ninside++;
     }
     if (ninside > 1) { fprintf(stderr, "bnb_b200: quantize LUT cell holds two thresholds\n"); abort(); }
-    if (ninside == 1) {
-      cells[c].thr = thr[inside];
-      cells[c].lo = (uint32_t)bucket_codes[inside];
-      cells[c].hi = (uint32_t)bucket_codes[inside + 1];
-    } else {
-      cells[c].thr = INFINITY;
-      cells[c].lo = cells[c].hi = (uint32_t)bucket_codes[nbelow];
-    }
-    cells[c].pad = 0;
+    q.base4[c] = (unsigned char)(4 * nbelow);
+  }
+  for (int j = 0; j < 16; j++) {
+    q.thr[j] = j < nthr ? thr[j] : INFINITY;
+    q.code[j] = (unsigned char)(j <= nthr ? bucket_codes[j] : 0);
   }
 }
 
@@ -70,8 +71,8 @@ static void build_host_tables() {
   static const float fp4_mag[8] = BNB_FP4_MAGNITUDES;
   int nf4_codes[16];
   for (int i = 0; i < 16; i++) nf4_codes[i] = i;
-  build_cells(h_qlut[1], nf4_thr, 15, nf4_codes);
-  build_cells(h_qlut[0], fp4_thr, 7, fp4_codes);
+  build_qtables(h_qtab[1], nf4_thr, 15, nf4_codes);
+  build_qtables(h_qtab[0], fp4_thr, 7, fp4_codes);
   for (int i = 0; i < 16; i++) h_dq4[1][i] = nf4_tab[i];
   for (int i = 0; i < 8; i++) { h_dq4[0][i] = fp4_mag[i]; h_dq4[0][i + 8] = -fp4_mag[i]; }
 }
@@ -84,26 +85,39 @@ void ensure_tables() {
   std::lock_guard<std::mutex> lock(g_lut_mutex);
   if (dev < 64 && g_lut_ready[dev]) return;
   std::call_once(h_lut_once, build_host_tables);
-  latch_error(cudaMemcpyToSymbol(g_qlut, h_qlut, sizeof(h_qlut)), "upload quantize LUT");
+  latch_error(cudaMemcpyToSymbol(g_qtab, h_qtab, sizeof(h_qtab)), "upload quantize LUT");
   latch_error(cudaMemcpyToSymbol(g_dq4_table, h_dq4, sizeof(h_dq4)), "upload dequant table");
   if (dev < 64) g_lut_ready[dev] = true;
 }
 
+// inv must be finite here (see quantize_store); |xn| <= 1 up to rounding, or NaN
 template <int QT>
-__device__ __forceinline__ uint32_t quantize4_lut(float xn, const QCell *lut) {
-  float ax = (QT == FP4) ? fabsf(xn) : xn;
-  float cl = fminf(fmaxf(ax, -1.0f), 1.0f);  // +-inf (denormal absmax) -> +-1: same bucket as the tree
-  uint32_t off = __float_as_uint(__fmaf_rn(cl, 1024.0f, 12583936.0f)) & 0xFF0u;  // 1.5*2^23 + 1024
-  const QCell c = *reinterpret_cast<const QCell *>(reinterpret_cast<const char *>(lut) + off);
-  uint32_t code = ax > c.thr ? c.hi : c.lo;
-  if (QT == FP4) code |= (xn < 0.0f) ? 8u : 0u;
-  return (xn != xn) ? 0u : code;  // every compare of the tree is false for NaN -> code 0
+__device__ __forceinline__ uint32_t quantize4_lut(float xn, const QTables *tab) {
+  if (QT == NF4) {
+    const float cl = fmaxf(xn, -1.0f);  // NaN -> -1 -> bucket 0
+    const uint32_t cell = __float_as_uint(__fmaf_rn(cl, 64.0f, 12582976.0f)) & 0xFFu;  // 1.5*2^23 + 64
+    const uint32_t b4 = tab->base4[cell];
+    const float t = *reinterpret_cast<const float *>(reinterpret_cast<const char *>(tab->thr) + b4);
+    return (b4 >> 2) + (cl > t ? 1u : 0u);
+  } else {
+    const float ax = fmaxf(fabsf(xn), 0.0f);  // NaN -> 0 -> bucket 0
+    const uint32_t cell = __float_as_uint(__fmaf_rn(ax, 64.0f, 12582976.0f)) & 0xFFu;
+    const uint32_t b4 = tab->base4[cell];
+    const float t = *reinterpret_cast<const float *>(reinterpret_cast<const char *>(tab->thr) + b4);
+    const uint32_t bucket = (b4 >> 2) + (ax > t ? 1u : 0u);
+    return tab->code[bucket] | ((xn < 0.0f) ? 8u : 0u);
+  }
+}
+template <int QT>
+__device__ __forceinline__ uint32_t quantize4_tree(float xn) {
+  return QT == NF4 ? quantize_nf4_tree(xn) : quantize_fp4_tree(xn);
 }
 
+// FINITE_INV == false: inv is +inf (absmax 0 or denormal) -> xn is +-inf / NaN, take the literal tree
 template <int QT>
-__device__ __forceinline__ uint32_t quantize_one(float xn, const QCell *lut, const float *code) {
+__device__ __forceinline__ uint32_t quantize_one(float xn, const QTables *lut, const float *code, bool finite_inv) {
   if (QT == General8bit) return quantize_8bit_search(code, xn);
-  return quantize4_lut<QT>(xn, lut);
+  return finite_inv ? quantize4_lut<QT>(xn, lut) : quantize4_tree<QT>(xn);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -126,17 +140,18 @@ __device__ __forceinline__ void load_vec(const T *A, long e0, long n, float (&x)
 // quantise E normalised values and store them (4-bit: E/2 bytes, 8-bit: E bytes)
 template <typename T, int QT, bool ALIGNED>
 __device__ __forceinline__ void quantize_store(const float (&x)[16 / sizeof(T)], float inv, long e0, long n,
-                                               unsigned char *out, const QCell *lut, const float *code) {
+                                               unsigned char *out, const QTables *lut, const float *code) {
   constexpr int E = 16 / sizeof(T);
   if (e0 >= n) return;
+  const bool fin = inv < INFINITY;  // uniform over the lanes of a quantisation block
   if (QT == General8bit) {
     uint32_t w[E / 4];
 #pragma unroll
     for (int j = 0; j < E / 4; j++) {
-      uint32_t b0 = quantize_one<QT>(__fmul_rn(x[4 * j + 0], inv), lut, code);
-      uint32_t b1 = quantize_one<QT>(__fmul_rn(x[4 * j + 1], inv), lut, code);
-      uint32_t b2 = quantize_one<QT>(__fmul_rn(x[4 * j + 2], inv), lut, code);
-      uint32_t b3 = quantize_one<QT>(__fmul_rn(x[4 * j + 3], inv), lut, code);
+      uint32_t b0 = quantize_one<QT>(__fmul_rn(x[4 * j + 0], inv), lut, code, fin);
+      uint32_t b1 = quantize_one<QT>(__fmul_rn(x[4 * j + 1], inv), lut, code, fin);
+      uint32_t b2 = quantize_one<QT>(__fmul_rn(x[4 * j + 2], inv), lut, code, fin);
+      uint32_t b3 = quantize_one<QT>(__fmul_rn(x[4 * j + 3], inv), lut, code, fin);
       w[j] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
     }
     if (ALIGNED && e0 + E <= n) {
@@ -151,8 +166,8 @@ __device__ __forceinline__ void quantize_store(const float (&x)[16 / sizeof(T)],
     uint32_t packed = 0;
 #pragma unroll
     for (int j = 0; j < E / 2; j++) {
-      uint32_t hi = quantize_one<QT>(__fmul_rn(x[2 * j], inv), lut, code);
-      uint32_t lo = quantize_one<QT>(__fmul_rn(x[2 * j + 1], inv), lut, code);
+      uint32_t hi = quantize_one<QT>(__fmul_rn(x[2 * j], inv), lut, code, fin);
+      uint32_t lo = quantize_one<QT>(__fmul_rn(x[2 * j + 1], inv), lut, code, fin);
       packed |= ((hi << 4) | lo) << (8 * j);
     }
     unsigned char *dst = out + (e0 >> 1);
@@ -168,12 +183,13 @@ __device__ __forceinline__ void quantize_store(const float (&x)[16 / sizeof(T)],
 }
 
 template <int QT>
-__device__ __forceinline__ void stage_tables(QCell *s_lut, float *s_code, const float *code) {
+__device__ __forceinline__ void stage_tables(QTables *s_lut, float *s_code, const float *code) {
   if (QT == General8bit) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_code[i] = code[i];
   } else {
-    const QCell *src = g_qlut[QT == NF4 ? 1 : 0];
-    for (int i = threadIdx.x; i < kQCells; i += blockDim.x) s_lut[i] = src[i];
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(&g_qtab[QT == NF4 ? 1 : 0]);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(s_lut);
+    for (int i = threadIdx.x; i < (int)(sizeof(QTables) / 4); i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
 }
@@ -187,7 +203,7 @@ __global__ void __launch_bounds__(256) k_quantize_small(const float *__restrict_
                                                         int blocksize, long n) {
   constexpr int E = 16 / sizeof(T);
   constexpr int U = 4;
-  __shared__ QCell s_lut[QT == General8bit ? 1 : kQCells];
+  __shared__ __align__(16) QTables s_lut[1];
   __shared__ float s_code[QT == General8bit ? 256 : 1];
   stage_tables<QT>(s_lut, s_code, code);
 
@@ -221,7 +237,7 @@ __global__ void __launch_bounds__(256) k_quantize_large(const float *__restrict_
                                                         float *__restrict__ absmax, unsigned char *__restrict__ out,
                                                         int blocksize, long n, long nblocks) {
   constexpr int E = 16 / sizeof(T);
-  __shared__ QCell s_lut[QT == General8bit ? 1 : kQCells];
+  __shared__ __align__(16) QTables s_lut[1];
   __shared__ float s_code[QT == General8bit ? 256 : 1];
   stage_tables<QT>(s_lut, s_code, code);
 
@@ -379,15 +395,17 @@ void dequantize_blockwise(const float *code, const unsigned char *A, const float
 // ------------------------------------------------------------------------------------------------
 template <int QT>
 __global__ void k_selftest_lut(unsigned long long *mismatches) {
-  __shared__ QCell s_lut[kQCells];
+  __shared__ __align__(16) QTables s_lut[1];
   stage_tables<QT>(s_lut, nullptr, nullptr);
   unsigned long long bad = 0;
   const unsigned long long total = 1ull << 32;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (unsigned long long)gridDim.x * blockDim.x) {
     float x = __uint_as_float((uint32_t)i);
-    uint32_t a = quantize4_lut<QT>(x, s_lut);
-    uint32_t b = (QT == NF4) ? quantize_nf4_tree(x) : quantize_fp4_tree(x);
+    // the LUT path is only taken for finite inv, i.e. |x| <= 1 (+ rounding slack) or NaN; test a superset
+    const bool in_domain = !(fabsf(x) > 1.0078125f);
+    uint32_t a = in_domain ? quantize4_lut<QT>(x, s_lut) : quantize4_tree<QT>(x);
+    uint32_t b = quantize4_tree<QT>(x);
     bad += (a != b);
   }
   if (bad) atomicAdd(mismatches, bad);

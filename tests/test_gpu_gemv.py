@@ -60,9 +60,11 @@ def test_gemv_config2_shapes(F, dtype, shape):
     assert err_exact <= TOL_EXACT[dtype], (err_exact,)
     assert rel_l2(yk, faithful) <= TOL_FAITHFUL[dtype]
     assert err_exact <= err_ref_chain * 1.05 + 1e-7, (err_exact, err_ref_chain)   # no less accurate than the reference
+    # elementwise: output rounding (half an ulp of T, relative) + the accumulated code/x rounding noise, which
+    # scales with the rms of the outputs (~5 sigma)
     rms = np.sqrt(np.mean(exact ** 2))
-    ulp = {"bf16": 2.0 ** -7, "fp16": 2.0 ** -10, "fp32": 2.0 ** -20}[dtype]
-    assert np.all(np.abs(yk - exact) <= ulp * np.abs(exact) + ulp / 2 * rms)
+    rel, noise = {"bf16": (2.0 ** -8, 2.0 ** -7), "fp16": (2.0 ** -11, 2.0 ** -9), "fp32": (1e-5, 1e-5)}[dtype]
+    assert np.all(np.abs(yk - exact) <= rel * np.abs(exact) + noise * rms)
 
 
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])
@@ -100,13 +102,15 @@ def test_gemv_3d_input_and_module_dispatch(F):
     lin = lin.cuda()
     assert lin.weight.dtype == torch.uint8 and lin.weight.quant_state.nested
     x = torch.randn(1, 1, 1024, dtype=torch.bfloat16, device="cuda")
-    y = lin(x)                                       # batch 1 -> gemv path
+    with torch.no_grad():
+        y = lin(x)                                   # batch 1 -> gemv path
     assert y.shape == (1, 1, 768)
     Wd = F.dequantize_4bit(lin.weight.data, lin.weight.quant_state).float()
     y_ref = x.float().reshape(1, -1) @ Wd.t() + ref_b.cuda().float()
     assert rel_l2(y.float().cpu().numpy(), y_ref.cpu().numpy()) < 5e-3
     xb = torch.randn(4, 7, 1024, dtype=torch.bfloat16, device="cuda")
-    yb = lin(xb)                                     # batch > 1 -> MatMul4Bit
+    with torch.no_grad():
+        yb = lin(xb)                                 # batch > 1 -> MatMul4Bit
     yb_ref = xb.float() @ Wd.t() + ref_b.cuda().float()
     assert yb.shape == (4, 7, 768)
     assert rel_l2(yb.float().cpu().numpy(), yb_ref.cpu().numpy()) < 5e-3
