@@ -17,6 +17,7 @@
 //   * a CTA owns 16 output rows, its 8 warps split K in 256-element chunks with register
 //     double-buffering (8 x 64-bit loads per lane in flight per chunk), deterministic smem reduction.
 // The MMA's n dimension carries the batch (1..8 activations rows) at no extra cost.
+#include <stdlib.h>
 #include <type_traits>
 
 #include "common.cuh"
@@ -55,6 +56,7 @@ template <> struct MmaT<__nv_bfloat16> {
 struct GemvArgs {
   int N, K, batch, blocksize;
   int bs_shift, bs2_shift;   // log2(blocksize), log2(blocksize2)
+  int flags;                 // bit 0: disable bulk L2 prefetch (experiments)
   const void *x;             // [batch, K] T
   const unsigned char *B;    // [N, K/2]
   const float *absmax;       // fp32 [N*K/blocksize]            (plain)
@@ -208,6 +210,476 @@ __global__ void __launch_bounds__(kGemvThreads) k_gemv4_mma(const GemvArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fast path: blocksize == 64, K % 256 == 0 (every shape of BASELINE configs 2 and 5).
+// Persistent CTA per SM (512 threads = 2 groups of 8 warps; a group owns one 16-row tile at a time and its
+// warps split K), hand-scheduled:
+//   * the byte LUT sits at a 64 KB-ALIGNED shared address, so ONE PRMT yields the complete lookup address
+//     (bytes 2,3 = table base, byte 1 = packed byte, byte 0 = lane*4) -- no add, no shift;
+//   * running pointers, no tail predicates, ping-pong register buffers, loads of the next (tile, chunk)
+//     issued before the current one is consumed -- also across tile boundaries;
+//   * absmax de-nested right before use; per-tile reduction through a 256-thread named barrier.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFastGroups = 2;
+constexpr int kFastThreads = kFastGroups * kGemvThreads;      // 512
+constexpr int kFastSmall = (kFastGroups * 2 * kGemvWarps * 128 + 256 + 16) * 4;  // s_red + s_code2 + s_codeT bytes
+constexpr int kFastSmem = 2 * 65536;                         // small arrays, then the table at the next 64 KB boundary
+
+template <bool NESTED> struct FastBuf {
+  uint2 w[4][2];
+  uint32_t q[2];   // nested: four uint8 absmax codes per row half
+  float am2[2];    // nested: absmax2 of the 256-group
+  float4 am4[2];   // plain: four fp32 absmax per row half
+};
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+
+template <typename T, bool NESTED, int EXP = 0>
+__global__ void __launch_bounds__(kFastThreads, 1) k_gemv4_fast(const GemvArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t lut_s = (smem_base + kFastSmall + 0xFFFFu) & ~0xFFFFu;   // 64 KB aligned shared address
+  unsigned char *s_lut = smem + (lut_s - smem_base);
+  float *s_red = reinterpret_cast<float *>(smem);             // [groups][2 parities][8 warps][128]
+  float *s_code2 = s_red + kFastGroups * 2 * kGemvWarps * 128;
+  uint32_t *s_codeT = reinterpret_cast<uint32_t *>(s_code2 + 256);
+  if (lut_s + 65536u > smem_base + kFastSmem) __trap();   // shared window base moved: layout no longer fits
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = warp >> 3, gw = warp & 7, gtid = tid & 255;
+  const int g = lane >> 2, t = lane & 3;
+  const int nchunks = a.K >> 8;
+  const int kb = a.K >> 6;  // absmax blocks per row
+  const int ntiles = (a.N + 15) >> 4;
+  const int tile_stride = gridDim.x * kFastGroups;
+  const float offset = a.offset;
+  const int bs2_shift = a.bs2_shift;
+  const T *xrow = reinterpret_cast<const T *>(a.x) + (size_t)min(g, a.batch - 1) * a.K + t * 16;
+
+  const uint2 *wp0, *wp1;
+  size_t blk0, blk1;
+  auto set_tile = [&](int tile, int c) {
+    const int row_lo = min(tile * 16 + g, a.N - 1), row_hi = min(tile * 16 + g + 8, a.N - 1);
+    wp0 = reinterpret_cast<const uint2 *>(a.B + (size_t)row_lo * (a.K >> 1)) + t + c * 16;
+    wp1 = reinterpret_cast<const uint2 *>(a.B + (size_t)row_hi * (a.K >> 1)) + t + c * 16;
+    blk0 = (size_t)row_lo * kb + c * 4;
+    blk1 = (size_t)row_hi * kb + c * 4;
+  };
+  // pull a whole 16-row tile (packed rows + its absmax run) into L2 with bulk prefetches: one instruction
+  // per row, no registers held -- this is what keeps tens of KB per SM in flight towards HBM
+  auto prefetch_tile = [&](int ptile) {
+    if (gw == 0 && ptile < ntiles && !(a.flags & 1)) {
+      const int prow = ptile * 16 + lane;
+      const uint32_t row_bytes = (uint32_t)(a.K >> 1);
+      if (lane < 16 && prow < a.N)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.B + (size_t)prow * row_bytes), "r"(row_bytes) : "memory");
+      if (lane == 16) {
+        const int rows = min(16, a.N - ptile * 16);
+        const size_t first = (size_t)ptile * 16 * kb;
+        if (NESTED) {
+          const uint32_t bytes = (uint32_t)((rows * kb) & ~15);
+          if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.qabsmax + first), "r"(bytes) : "memory");
+        } else {
+          const uint32_t bytes = (uint32_t)(rows * kb * 4);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.absmax + first), "r"(bytes) : "memory");
+        }
+      }
+    }
+  };
+  auto load = [&](FastBuf<NESTED> &b) {
+    if (EXP == 2) {  // experiment: no global weight traffic
+#pragma unroll
+      for (int s = 0; s < 4; s++) { b.w[s][0] = make_uint2(tid * 2654435761u + s, tid ^ 0x5bd1e995u); b.w[s][1] = make_uint2(tid * 40503u + s, tid * 97u); }
+      b.q[0] = b.q[1] = 0x80818283u; b.am2[0] = b.am2[1] = 1.0f; b.am4[0] = b.am4[1] = make_float4(1.f, 1.f, 1.f, 1.f);
+      return;
+    }
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      b.w[s][0] = ld_stream_u2(wp0 + s * 4);
+      b.w[s][1] = ld_stream_u2(wp1 + s * 4);
+    }
+    if (NESTED) {
+      b.q[0] = __ldg(reinterpret_cast<const uint32_t *>(a.qabsmax + blk0));
+      b.q[1] = __ldg(reinterpret_cast<const uint32_t *>(a.qabsmax + blk1));
+      b.am2[0] = __ldg(a.absmax2 + (blk0 >> bs2_shift));
+      b.am2[1] = __ldg(a.absmax2 + (blk1 >> bs2_shift));
+    } else {
+      b.am4[0] = __ldg(reinterpret_cast<const float4 *>(a.absmax + blk0));
+      b.am4[1] = __ldg(reinterpret_cast<const float4 *>(a.absmax + blk1));
+    }
+    wp0 += kGemvWarps * 16;
+    wp1 += kGemvWarps * 16;
+    blk0 += kGemvWarps * 4;
+    blk1 += kGemvWarps * 4;
+  };
+
+  if (NESTED && tid < 256) s_code2[tid] = a.code2[tid];
+  if (tid < 16) s_codeT[tid] = MmaT<T>::pack(a.code[tid], 0.0f) & 0xFFFFu;
+
+  FastBuf<NESTED> bufA, bufB;
+  int tile = blockIdx.x * kFastGroups + grp, c = gw;
+  prefetch_tile(tile);
+  prefetch_tile(tile + tile_stride);
+  if (tile < ntiles && c < nchunks) { set_tile(tile, c); load(bufA); }  // in flight while the table is built
+  __syncthreads();
+  {
+    // byte e -> {T(code[e>>4]), T(code[e&15])}, replicated for the 32 lanes: entry stride 256 B, 128 B used.
+    // lanes 8i..8i+7 of a warp write one entry (8 x 16 B = its 128 B): conflict-free 128-bit stores.
+    const int j = tid & 7, esub = tid >> 3;  // 64 entries per pass
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int e = i * 64 + esub;
+      const uint32_t v = s_codeT[e >> 4] | (s_codeT[e & 15] << 16);
+      *reinterpret_cast<uint4 *>(s_lut + e * 256 + j * 16) = make_uint4(v, v, v, v);
+    }
+  }
+  __syncthreads();
+
+  const uint32_t lutlane = lut_s | (uint32_t)(lane * 4);   // PRMT operand b: bytes 0,2,3 of every lookup address
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int parity = 0;
+  const bool has_x = g < a.batch;
+  uint4 xa = make_uint4(0, 0, 0, 0), xb = make_uint4(0, 0, 0, 0);
+
+  auto compute = [&](const FastBuf<NESTED> &b, int cc) {
+    if (EXP == 1) {  // experiment: memory stream only
+      uint32_t z = 0;
+#pragma unroll
+      for (int s = 0; s < 4; s++) z ^= b.w[s][0].x ^ b.w[s][0].y ^ b.w[s][1].x ^ b.w[s][1].y;
+      acc[0] += __uint_as_float(z & 0x3fffffffu) + (NESTED ? __uint_as_float(b.q[0] & 0x3fffffu) + b.am2[1] : b.am4[0].x);
+      return;
+    }
+    float am[4][2];
+    if (NESTED) {
+#pragma unroll
+      for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+          am[s][h] = __fadd_rn(__fmul_rn(s_code2[(b.q[h] >> (8 * s)) & 0xFFu], b.am2[h]), offset);
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; h++) { am[0][h] = b.am4[h].x; am[1][h] = b.am4[h].y; am[2][h] = b.am4[h].z; am[3][h] = b.am4[h].w; }
+    }
+    const uint4 *x4 = reinterpret_cast<const uint4 *>(xrow + (size_t)cc * 256);
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      // only the lanes that own a real activation row (g < batch) load x: the others feed ignored MMA
+      // columns with whatever their registers hold, and cost no L1 write-back bandwidth
+      if (has_x) { xa = __ldg(x4 + s * 8); xb = __ldg(x4 + s * 8 + 1); }
+      const uint32_t xr[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+      const uint32_t wl[2] = {b.w[s][0].x, b.w[s][0].y};
+      const uint32_t wh[2] = {b.w[s][1].x, b.w[s][1].y};
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        // selector 0x76b4: result = {lutlane.b0, w.byte b, lutlane.b2, lutlane.b3} = table + byte*256 + lane*4
+        const uint32_t src_l = wl[i >> 1], src_h = wh[i >> 1];
+        const uint32_t sel0 = (i & 1) ? 0x7624u : 0x7604u, sel1 = (i & 1) ? 0x7634u : 0x7614u;
+        uint32_t af[4];
+        af[0] = lds_u32(__byte_perm(src_l, lutlane, sel0));
+        af[2] = lds_u32(__byte_perm(src_l, lutlane, sel1));
+        af[1] = lds_u32(__byte_perm(src_h, lutlane, sel0));
+        af[3] = lds_u32(__byte_perm(src_h, lutlane, sel1));
+        MmaT<T>::mma(d, af, xr[2 * i], xr[2 * i + 1]);
+      }
+      acc[0] = __fmaf_rn(d[0], am[s][0], acc[0]);
+      acc[1] = __fmaf_rn(d[1], am[s][0], acc[1]);
+      acc[2] = __fmaf_rn(d[2], am[s][1], acc[2]);
+      acc[3] = __fmaf_rn(d[3], am[s][1], acc[3]);
+    }
+  };
+
+  // finish a tile: deterministic cross-warp reduction inside the group (double-buffered by parity)
+  auto finish_tile = [&](int done_tile) {
+    float *red = s_red + ((grp * 2 + parity) * kGemvWarps) * 128;
+    float *mine = red + gw * 128;
+    mine[g * 8 + 2 * t] = acc[0];
+    mine[g * 8 + 2 * t + 1] = acc[1];
+    mine[(g + 8) * 8 + 2 * t] = acc[2];
+    mine[(g + 8) * 8 + 2 * t + 1] = acc[3];
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
+    if (gtid < 16 * a.batch) {
+      const int row = gtid & 15, col = gtid >> 4;
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < kGemvWarps; w++) sum += red[w * 128 + row * 8 + col];
+      const int r = done_tile * 16 + row;
+      if (r < a.N) reinterpret_cast<T *>(a.out)[(size_t)col * a.N + r] = from_float<T>(sum);
+    }
+    parity ^= 1;
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+  };
+
+  // one pipeline step: prefetch the next (tile, chunk) into `nxt`, consume `cur`
+  auto step = [&](const FastBuf<NESTED> &cur, FastBuf<NESTED> &nxt) {
+    int nc = c + kGemvWarps, ntile = tile;
+    if (nc >= nchunks) { nc = gw; ntile = tile + tile_stride; }
+    if (ntile < ntiles && nc < nchunks) {
+      if (ntile != tile) { set_tile(ntile, nc); prefetch_tile(ntile + tile_stride); }
+      load(nxt);
+    }
+    if (c < nchunks) compute(cur, c);
+    if (ntile != tile) finish_tile(tile);
+    tile = ntile;
+    c = nc;
+  };
+
+  while (tile < ntiles) {
+    step(bufA, bufB);
+    if (tile >= ntiles) break;
+    step(bufB, bufA);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA-staged, warp-specialised fast path (blocksize 64, K % 256 == 0).  One persistent CTA per SM:
+//   warp 16      : PRODUCER -- cp.async.bulk (TMA 1-D) copies of packed rows into a 3-stage shared-memory ring
+//                  per consumer group, completion on mbarriers (complete_tx); runs up to 3 stages
+//                  (48 KB per group) ahead of the consumers, so ~96 KB per SM is in flight towards HBM;
+//   warps 0..15  : CONSUMERS, two groups of 8 warps; a group owns one 16-row tile at a time, a stage is a
+//                  2048-element K slab of it (1 KB per row, one 256-element chunk per warp).
+// Rows are stored with a 1056-byte pitch so the 64-bit fragment reads are bank-conflict-free; the dequant
+// LUT, MMA and absmax handling are those of k_gemv4_fast.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTmaConsumers = 16;
+constexpr int kTmaThreads = (kTmaConsumers + 1) * 32;   // 544
+constexpr int kTmaStages = 3;
+constexpr int kSlabK = 2048;                            // K elements per stage
+constexpr int kRowPitch = kSlabK / 2 + 32;              // 1056 B
+constexpr int kStageBytes = 16 * kRowPitch;             // 16896 B
+constexpr int kRingBytes = kTmaStages * kStageBytes;    // 50688 B
+constexpr int kTmaHead = 256 + 64 + 1024 + 192;         // barriers, codeT, code2, pad -> 1536 B
+constexpr int kTmaRedBytes = kFastGroups * 2 * kGemvWarps * 128 * 4;   // 16 KB
+constexpr int kTmaSmem = 65536 /*region A (<= 63 KB used)*/ + 65536 /*LUT*/ + kRingBytes + kTmaRedBytes;
+
+__device__ __forceinline__ uint2 lds_u64(uint32_t saddr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void mbar_init_(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  long long t0 = 0;
+  for (int spin = 0;; spin++) {
+    asm volatile("{\n .reg .pred P;\n mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n selp.u32 %0, 1, 0, P;\n}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+    if (spin == 64) t0 = clock64();
+    if (spin > 64 && clock64() - t0 > 2000000000ll) __trap();   // protocol bug: fail, never hang
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <typename T, bool NESTED>
+__global__ void __launch_bounds__(kTmaThreads, 1) k_gemv4_tma(const GemvArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t lut_s = (smem_base + kTmaHead + kRingBytes + 0xFFFFu) & ~0xFFFFu;
+  if (lut_s + 65536u + kRingBytes + kTmaRedBytes > smem_base + kTmaSmem) __trap();
+  // region A (before the table): barriers | codeT | code2 | ring of group 0
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);                       // full[2][3], empty[2][3]
+  uint32_t *s_codeT = reinterpret_cast<uint32_t *>(smem + 256);
+  float *s_code2 = reinterpret_cast<float *>(smem + 256 + 64);
+  const uint32_t ring_s[2] = {smem_base + kTmaHead, lut_s + 65536u};
+  unsigned char *s_lut = smem + (lut_s - smem_base);
+  float *s_red = reinterpret_cast<float *>(smem + (lut_s - smem_base) + 65536 + kRingBytes);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nchunks = a.K >> 8;
+  const int nslabs = (a.K + kSlabK - 1) / kSlabK;
+  const int kb = a.K >> 6;
+  const int ntiles = (a.N + 15) >> 4;
+  const int tile_stride = gridDim.x * kFastGroups;
+  const uint32_t row_bytes = (uint32_t)(a.K >> 1);
+
+  if (tid == 0) {
+    for (int i = 0; i < 2 * kTmaStages; i++) {
+      mbar_init_(smem_base + i * 8, 1);                              // full: producer's expect_tx arrival
+      mbar_init_(smem_base + (2 * kTmaStages + i) * 8, kGemvWarps);  // empty: one arrival per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (NESTED && tid < 256) s_code2[tid] = a.code2[tid];
+  if (tid < 16) s_codeT[tid] = MmaT<T>::pack(a.code[tid], 0.0f) & 0xFFFFu;
+  __syncthreads();
+
+  if (warp == kTmaConsumers) {
+    // ===================== producer =====================
+    if (lane < 16) {
+      int n[2] = {0, 0};
+      int tile[2] = {(int)blockIdx.x * kFastGroups, (int)blockIdx.x * kFastGroups + 1};
+      int slab[2] = {0, 0};
+      while (tile[0] < ntiles || tile[1] < ntiles) {
+#pragma unroll
+        for (int grp = 0; grp < 2; grp++) {
+          if (tile[grp] >= ntiles) continue;
+          const int slot = n[grp] % kTmaStages;
+          const uint32_t parity = (uint32_t)(n[grp] / kTmaStages) & 1u;
+          const uint32_t full = smem_base + (grp * kTmaStages + slot) * 8;
+          const uint32_t empty = smem_base + (2 * kTmaStages + grp * kTmaStages + slot) * 8;
+          mbar_wait_(empty, parity ^ 1u);
+          const uint32_t off = (uint32_t)slab[grp] * (kSlabK / 2);
+          const uint32_t bytes = min((uint32_t)(kSlabK / 2), row_bytes - off);
+          if (lane == 0) mbar_expect_tx_(full, 16u * bytes);
+          __syncwarp(0x0000ffffu);
+          const int row = min(tile[grp] * 16 + lane, a.N - 1);
+          bulk_g2s(ring_s[grp] + slot * kStageBytes + lane * kRowPitch, a.B + (size_t)row * row_bytes + off, bytes, full);
+          n[grp]++;
+          if (++slab[grp] == nslabs) { slab[grp] = 0; tile[grp] += tile_stride; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===================== consumers =====================
+  // build the byte LUT (16 consumer warps = 512 threads), then a consumer-only barrier
+  {
+    const int j = tid & 7, esub = tid >> 3;  // 64 entries per pass
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int e = i * 64 + esub;
+      const uint32_t v = s_codeT[e >> 4] | (s_codeT[e & 15] << 16);
+      *reinterpret_cast<uint4 *>(s_lut + e * 256 + j * 16) = make_uint4(v, v, v, v);
+    }
+  }
+  asm volatile("bar.sync 3, 512;" ::: "memory");
+
+  const int grp = warp >> 3, gw = warp & 7, gtid = tid & 255;
+  const int g = lane >> 2, t = lane & 3;
+  const float offset = a.offset;
+  const int bs2_shift = a.bs2_shift;
+  const T *xrow = reinterpret_cast<const T *>(a.x) + (size_t)min(g, a.batch - 1) * a.K + t * 16;
+  const bool has_x = g < a.batch;
+  uint4 xa = make_uint4(0, 0, 0, 0), xb = make_uint4(0, 0, 0, 0);
+  const uint32_t lutlane = lut_s | (uint32_t)(lane * 4);
+  // this lane's fragment position inside a stage: rows g / g+8, its warp's 128-byte chunk, 8 bytes per step
+  const uint32_t frag_off = (uint32_t)g * kRowPitch + (uint32_t)gw * 128 + (uint32_t)t * 8;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int parity_red = 0;
+  int n = 0;
+
+  // absmax of (tile, slab) for this warp's chunk, rows g and g+8 (registers, fetched one stage ahead)
+  struct Abs { uint32_t q[2]; float am2[2]; float4 am4[2]; };
+  auto load_abs = [&](Abs &ab, int tile, int slab) {
+    const int c = slab * (kSlabK / 256) + gw;
+    if (tile >= ntiles || c >= nchunks) return;
+    const int row_lo = min(tile * 16 + g, a.N - 1), row_hi = min(tile * 16 + g + 8, a.N - 1);
+    const size_t b0 = (size_t)row_lo * kb + c * 4, b1 = (size_t)row_hi * kb + c * 4;
+    if (NESTED) {
+      ab.q[0] = __ldg(reinterpret_cast<const uint32_t *>(a.qabsmax + b0));
+      ab.q[1] = __ldg(reinterpret_cast<const uint32_t *>(a.qabsmax + b1));
+      ab.am2[0] = __ldg(a.absmax2 + (b0 >> bs2_shift));
+      ab.am2[1] = __ldg(a.absmax2 + (b1 >> bs2_shift));
+    } else {
+      ab.am4[0] = __ldg(reinterpret_cast<const float4 *>(a.absmax + b0));
+      ab.am4[1] = __ldg(reinterpret_cast<const float4 *>(a.absmax + b1));
+    }
+  };
+
+  auto consume = [&](const Abs &ab, int slab, uint32_t stage_s) {
+    const int c = slab * (kSlabK / 256) + gw;
+    if (c >= nchunks) return;   // partial last slab: this warp has no chunk
+    float am[4][2];
+    if (NESTED) {
+#pragma unroll
+      for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+          am[s][h] = __fadd_rn(__fmul_rn(s_code2[(ab.q[h] >> (8 * s)) & 0xFFu], ab.am2[h]), offset);
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; h++) { am[0][h] = ab.am4[h].x; am[1][h] = ab.am4[h].y; am[2][h] = ab.am4[h].z; am[3][h] = ab.am4[h].w; }
+    }
+    const uint4 *x4 = reinterpret_cast<const uint4 *>(xrow + (size_t)c * 256);
+    const uint32_t fs = stage_s + frag_off;
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      if (has_x) { xa = __ldg(x4 + s * 8); xb = __ldg(x4 + s * 8 + 1); }
+      const uint32_t xr[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+      const uint2 w_lo = lds_u64(fs + s * 32), w_hi = lds_u64(fs + 8 * kRowPitch + s * 32);
+      const uint32_t wl[2] = {w_lo.x, w_lo.y};
+      const uint32_t wh[2] = {w_hi.x, w_hi.y};
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint32_t src_l = wl[i >> 1], src_h = wh[i >> 1];
+        const uint32_t sel0 = (i & 1) ? 0x7624u : 0x7604u, sel1 = (i & 1) ? 0x7634u : 0x7614u;
+        uint32_t af[4];
+        af[0] = lds_u32(__byte_perm(src_l, lutlane, sel0));
+        af[2] = lds_u32(__byte_perm(src_l, lutlane, sel1));
+        af[1] = lds_u32(__byte_perm(src_h, lutlane, sel0));
+        af[3] = lds_u32(__byte_perm(src_h, lutlane, sel1));
+        MmaT<T>::mma(d, af, xr[2 * i], xr[2 * i + 1]);
+      }
+      acc[0] = __fmaf_rn(d[0], am[s][0], acc[0]);
+      acc[1] = __fmaf_rn(d[1], am[s][0], acc[1]);
+      acc[2] = __fmaf_rn(d[2], am[s][1], acc[2]);
+      acc[3] = __fmaf_rn(d[3], am[s][1], acc[3]);
+    }
+  };
+
+  auto finish_tile = [&](int done_tile) {
+    float *red = s_red + ((grp * 2 + parity_red) * kGemvWarps) * 128;
+    float *mine = red + gw * 128;
+    mine[g * 8 + 2 * t] = acc[0];
+    mine[g * 8 + 2 * t + 1] = acc[1];
+    mine[(g + 8) * 8 + 2 * t] = acc[2];
+    mine[(g + 8) * 8 + 2 * t + 1] = acc[3];
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
+    if (gtid < 16 * a.batch) {
+      const int row = gtid & 15, col = gtid >> 4;
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < kGemvWarps; w++) sum += red[w * 128 + row * 8 + col];
+      const int r = done_tile * 16 + row;
+      if (r < a.N) reinterpret_cast<T *>(a.out)[(size_t)col * a.N + r] = from_float<T>(sum);
+    }
+    parity_red ^= 1;
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+  };
+
+  int tile = blockIdx.x * kFastGroups + grp, slab = 0;
+  Abs abA, abB;
+  load_abs(abA, tile, 0);
+  auto stage_step = [&](const Abs &cur, Abs &nxt) {
+    int nslab = slab + 1, ntile = tile;
+    if (nslab == nslabs) { nslab = 0; ntile = tile + tile_stride; }
+    load_abs(nxt, ntile, nslab);
+    const int slot = n % kTmaStages;
+    const uint32_t parity = (uint32_t)(n / kTmaStages) & 1u;
+    mbar_wait_(smem_base + (grp * kTmaStages + slot) * 8, parity);
+    consume(cur, slab, ring_s[grp] + slot * kStageBytes);
+    __syncwarp();
+    if (lane == 0) mbar_arrive_(smem_base + (2 * kTmaStages + grp * kTmaStages + slot) * 8);
+    if (ntile != tile) finish_tile(tile);
+    n++;
+    tile = ntile;
+    slab = nslab;
+  };
+  while (tile < ntiles) {
+    stage_step(abA, abB);
+    if (tile >= ntiles) break;
+    stage_step(abB, abA);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // generic path: any K / ldb / blocksize / dtype (incl. fp32).  One warp per row, 16 packed bytes per
 // lane per step, fp32 math.  Semantics of the tail follow kernel_gemm.cpp:1312-1366: bytes at index
 // >= K/2 read as 0x77 and activations past K as 0.
@@ -255,15 +727,46 @@ static int ilog2(int v) { int s = 0; while ((1 << s) < v) s++; return s; }
 template <typename T, bool NESTED, bool VEC4>
 static void launch_mma_inst(const GemvArgs &a) {
   static bool attr_set[64] = {false};
-  const size_t smem = kGemvLutBytes + kGemvWarps * 128 * sizeof(float) + 256 * sizeof(float) + 16 * sizeof(uint32_t);
+  static int num_sms[64] = {0};
+  const size_t smem = VEC4 ? (size_t)kFastSmem
+                           : kGemvLutBytes + kGemvWarps * 128 * sizeof(float) + 256 * sizeof(float) + 16 * sizeof(uint32_t);
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 64 && !attr_set[dev]) {
-    latch_error(cudaFuncSetAttribute(k_gemv4_mma<T, NESTED, VEC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                "gemv smem attr");
+  dev = dev < 64 ? dev : 63;
+  auto kernel = VEC4 ? k_gemv4_fast<T, NESTED> : k_gemv4_mma<T, NESTED, false>;
+  static int exp_mode = -1, pf_off = 0;
+  if (exp_mode < 0) {
+    const char *e = getenv("BNB_B200_GEMV_EXP"); exp_mode = e ? atoi(e) : 0;
+    const char *f = getenv("BNB_B200_GEMV_PF"); pf_off = (f && f[0] == '0') ? 1 : 0;
+  }
+  GemvArgs a2 = a;
+  a2.flags = pf_off;
+  if (VEC4 && NESTED && exp_mode == 1) kernel = k_gemv4_fast<T, NESTED, 1>;
+  if (VEC4 && NESTED && exp_mode == 2) kernel = k_gemv4_fast<T, NESTED, 2>;
+  if (!attr_set[dev]) {
+    latch_error(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "gemv smem attr");
+    cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
     attr_set[dev] = true;
   }
-  k_gemv4_mma<T, NESTED, VEC4><<<ceil_div(a.N, 16), kGemvThreads, smem, current_stream()>>>(a);
+  static int impl_reg = -1;
+  if (impl_reg < 0) { const char *e = getenv("BNB_B200_GEMV_IMPL"); impl_reg = (e && e[0] == 'r') ? 1 : 0; }
+  if (VEC4 && !impl_reg && exp_mode == 0) {
+    static bool attr2[64] = {false};
+    if (!attr2[dev]) {
+      latch_error(cudaFuncSetAttribute(k_gemv4_tma<T, NESTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmem), "gemv tma smem attr");
+      attr2[dev] = true;
+    }
+    const int ctas = ceil_div(ceil_div(a.N, 16), kFastGroups);
+    const int grid = ctas < num_sms[dev] ? ctas : num_sms[dev];
+    k_gemv4_tma<T, NESTED><<<grid, kTmaThreads, kTmaSmem, current_stream()>>>(a2);
+  } else if (VEC4) {
+    const int tiles = ceil_div(a.N, 16);
+    const int ctas = ceil_div(tiles, kFastGroups);
+    const int grid = ctas < num_sms[dev] ? ctas : num_sms[dev];
+    kernel<<<grid, kFastThreads, smem, current_stream()>>>(a2);
+  } else {
+    kernel<<<ceil_div(a.N, 16), kGemvThreads, smem, current_stream()>>>(a);
+  }
   check_launch("gemv_4bit (mma)");
 }
 
