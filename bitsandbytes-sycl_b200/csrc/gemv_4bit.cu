@@ -444,7 +444,8 @@ __global__ void __launch_bounds__(kFastThreads, 1) k_gemv4_fast(const GemvArgs a
 // Rows are stored with a 1056-byte pitch so the 64-bit fragment reads are bank-conflict-free; the dequant
 // LUT, MMA and absmax handling are those of k_gemv4_fast.
 // ------------------------------------------------------------------------------------------------
-constexpr int kTmaConsumers = 16;
+constexpr int kTmaGroups = 2;                           // consumer groups of 8 warps (3 x 2 stages measured slower)
+constexpr int kTmaConsumers = kTmaGroups * kGemvWarps;  // 16 warps
 constexpr int kTmaThreads = (kTmaConsumers + 1) * 32;   // 544
 constexpr int kTmaStages = 3;
 constexpr int kSlabK = 2048;                            // K elements per stage
@@ -452,8 +453,11 @@ constexpr int kRowPitch = kSlabK / 2 + 32;              // 1056 B
 constexpr int kStageBytes = 16 * kRowPitch;             // 16896 B
 constexpr int kRingBytes = kTmaStages * kStageBytes;    // 50688 B
 constexpr int kTmaHead = 256 + 64 + 1024 + 192;         // barriers, codeT, code2, pad -> 1536 B
-constexpr int kTmaRedBytes = kFastGroups * 2 * kGemvWarps * 128 * 4;   // 16 KB
-constexpr int kTmaSmem = 65536 /*region A (<= 63 KB used)*/ + 65536 /*LUT*/ + kRingBytes + kTmaRedBytes;
+constexpr int kTmaRedBytes = kTmaGroups * 2 * kGemvWarps * 128 * 4;    // 24 KB
+// region A (before the 64 KB-aligned table): head + ring of group 0; region B (after it): rings of groups 1.. + s_red
+constexpr int kTmaSmem = 65536 + 65536 + (kTmaGroups - 1) * kRingBytes + kTmaRedBytes;
+static_assert(kTmaHead + kRingBytes <= 65536 - 1024, "region A overflows");
+static_assert(kTmaSmem <= 227 * 1024, "too much shared memory");
 
 __device__ __forceinline__ uint2 lds_u64(uint32_t saddr) {
   uint2 v;
@@ -490,27 +494,29 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gemv4_tma(const GemvArgs a) 
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
   const uint32_t lut_s = (smem_base + kTmaHead + kRingBytes + 0xFFFFu) & ~0xFFFFu;
-  if (lut_s + 65536u + kRingBytes + kTmaRedBytes > smem_base + kTmaSmem) __trap();
+  if (lut_s + 65536u + (kTmaGroups - 1) * kRingBytes + kTmaRedBytes > smem_base + kTmaSmem) __trap();
   // region A (before the table): barriers | codeT | code2 | ring of group 0
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);                       // full[2][3], empty[2][3]
   uint32_t *s_codeT = reinterpret_cast<uint32_t *>(smem + 256);
   float *s_code2 = reinterpret_cast<float *>(smem + 256 + 64);
-  const uint32_t ring_s[2] = {smem_base + kTmaHead, lut_s + 65536u};
+  uint32_t ring_s[kTmaGroups];
+  ring_s[0] = smem_base + kTmaHead;
+#pragma unroll
+  for (int i = 1; i < kTmaGroups; i++) ring_s[i] = lut_s + 65536u + (i - 1) * kRingBytes;
   unsigned char *s_lut = smem + (lut_s - smem_base);
-  float *s_red = reinterpret_cast<float *>(smem + (lut_s - smem_base) + 65536 + kRingBytes);
+  float *s_red = reinterpret_cast<float *>(smem + (lut_s - smem_base) + 65536 + (kTmaGroups - 1) * kRingBytes);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nchunks = a.K >> 8;
   const int nslabs = (a.K + kSlabK - 1) / kSlabK;
   const int kb = a.K >> 6;
   const int ntiles = (a.N + 15) >> 4;
-  const int tile_stride = gridDim.x * kFastGroups;
+  const int tile_stride = gridDim.x * kTmaGroups;
   const uint32_t row_bytes = (uint32_t)(a.K >> 1);
 
   if (tid == 0) {
-    for (int i = 0; i < 2 * kTmaStages; i++) {
-      mbar_init_(smem_base + i * 8, 1);                              // full: producer's expect_tx arrival
-      mbar_init_(smem_base + (2 * kTmaStages + i) * 8, kGemvWarps);  // empty: one arrival per consumer warp
+    for (int i = 0; i < kTmaGroups * kTmaStages; i++) {
+      mbar_init_(smem_base + i * 8, 1);                                       // full: producer's expect_tx arrival
+      mbar_init_(smem_base + (kTmaGroups * kTmaStages + i) * 8, kGemvWarps);  // empty: one arrival per consumer warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -521,17 +527,20 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gemv4_tma(const GemvArgs a) 
   if (warp == kTmaConsumers) {
     // ===================== producer =====================
     if (lane < 16) {
-      int n[2] = {0, 0};
-      int tile[2] = {(int)blockIdx.x * kFastGroups, (int)blockIdx.x * kFastGroups + 1};
-      int slab[2] = {0, 0};
-      while (tile[0] < ntiles || tile[1] < ntiles) {
+      int n[kTmaGroups], tile[kTmaGroups], slab[kTmaGroups];
 #pragma unroll
-        for (int grp = 0; grp < 2; grp++) {
+      for (int i = 0; i < kTmaGroups; i++) { n[i] = 0; slab[i] = 0; tile[i] = (int)blockIdx.x * kTmaGroups + i; }
+      bool any = true;
+      while (any) {
+        any = false;
+#pragma unroll
+        for (int grp = 0; grp < kTmaGroups; grp++) {
           if (tile[grp] >= ntiles) continue;
+          any = true;
           const int slot = n[grp] % kTmaStages;
           const uint32_t parity = (uint32_t)(n[grp] / kTmaStages) & 1u;
           const uint32_t full = smem_base + (grp * kTmaStages + slot) * 8;
-          const uint32_t empty = smem_base + (2 * kTmaStages + grp * kTmaStages + slot) * 8;
+          const uint32_t empty = smem_base + (kTmaGroups * kTmaStages + grp * kTmaStages + slot) * 8;
           mbar_wait_(empty, parity ^ 1u);
           const uint32_t off = (uint32_t)slab[grp] * (kSlabK / 2);
           const uint32_t bytes = min((uint32_t)(kSlabK / 2), row_bytes - off);
@@ -548,17 +557,15 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gemv4_tma(const GemvArgs a) 
   }
 
   // ===================== consumers =====================
-  // build the byte LUT (16 consumer warps = 512 threads), then a consumer-only barrier
+  // build the byte LUT with all consumer threads, then a consumer-only barrier
   {
-    const int j = tid & 7, esub = tid >> 3;  // 64 entries per pass
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int e = i * 64 + esub;
+    const int j = tid & 7;
+    for (int e = tid >> 3; e < 256; e += kTmaConsumers * 4) {
       const uint32_t v = s_codeT[e >> 4] | (s_codeT[e & 15] << 16);
       *reinterpret_cast<uint4 *>(s_lut + e * 256 + j * 16) = make_uint4(v, v, v, v);
     }
   }
-  asm volatile("bar.sync 3, 512;" ::: "memory");
+  asm volatile("bar.sync %0, %1;" ::"r"(kTmaGroups + 1), "r"(kTmaConsumers * 32) : "memory");
 
   const int grp = warp >> 3, gw = warp & 7, gtid = tid & 255;
   const int g = lane >> 2, t = lane & 3;
@@ -654,7 +661,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gemv4_tma(const GemvArgs a) 
     acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
   };
 
-  int tile = blockIdx.x * kFastGroups + grp, slab = 0;
+  int tile = blockIdx.x * kTmaGroups + grp, slab = 0;
   Abs abA, abB;
   load_abs(abA, tile, 0);
   auto stage_step = [&](const Abs &cur, Abs &nxt) {
@@ -666,7 +673,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gemv4_tma(const GemvArgs a) 
     mbar_wait_(smem_base + (grp * kTmaStages + slot) * 8, parity);
     consume(cur, slab, ring_s[grp] + slot * kStageBytes);
     __syncwarp();
-    if (lane == 0) mbar_arrive_(smem_base + (2 * kTmaStages + grp * kTmaStages + slot) * 8);
+    if (lane == 0) mbar_arrive_(smem_base + (kTmaGroups * kTmaStages + grp * kTmaStages + slot) * 8);
     if (ntile != tile) finish_tile(tile);
     n++;
     tile = ntile;
@@ -756,7 +763,7 @@ static void launch_mma_inst(const GemvArgs &a) {
       latch_error(cudaFuncSetAttribute(k_gemv4_tma<T, NESTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmem), "gemv tma smem attr");
       attr2[dev] = true;
     }
-    const int ctas = ceil_div(ceil_div(a.N, 16), kFastGroups);
+    const int ctas = ceil_div(ceil_div(a.N, 16), kTmaGroups);
     const int grid = ctas < num_sms[dev] ? ctas : num_sms[dev];
     k_gemv4_tma<T, NESTED><<<grid, kTmaThreads, kTmaSmem, current_stream()>>>(a2);
   } else if (VEC4) {

@@ -164,11 +164,20 @@ __device__ __forceinline__ void quantize_store(const float (&x)[16 / sizeof(T)],
     }
   } else {
     uint32_t packed = 0;
+    if (fin) {  // straight-line fast path: every lane of the block takes it together
 #pragma unroll
-    for (int j = 0; j < E / 2; j++) {
-      uint32_t hi = quantize_one<QT>(__fmul_rn(x[2 * j], inv), lut, code, fin);
-      uint32_t lo = quantize_one<QT>(__fmul_rn(x[2 * j + 1], inv), lut, code, fin);
-      packed |= ((hi << 4) | lo) << (8 * j);
+      for (int j = 0; j < E / 2; j++) {
+        const uint32_t hi = quantize4_lut<QT>(__fmul_rn(x[2 * j], inv), lut);
+        const uint32_t lo = quantize4_lut<QT>(__fmul_rn(x[2 * j + 1], inv), lut);
+        packed |= ((hi << 4) | lo) << (8 * j);
+      }
+    } else {    // absmax 0 / denormal: inv = +inf, x*inv is +-inf or NaN -> the literal decision tree
+#pragma unroll 1
+      for (int j = 0; j < E / 2; j++) {
+        const uint32_t hi = quantize4_tree<QT>(__fmul_rn(x[2 * j], inv));
+        const uint32_t lo = quantize4_tree<QT>(__fmul_rn(x[2 * j + 1], inv));
+        packed |= ((hi << 4) | lo) << (8 * j);
+      }
     }
     unsigned char *dst = out + (e0 >> 1);
     if (ALIGNED && e0 + E <= n) {
@@ -266,6 +275,59 @@ __global__ void __launch_bounds__(256) k_quantize_large(const float *__restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1 bulk: the branch-free body for 4-bit quantisation at blocksize <= 32*E on 16-byte aligned tensors.
+// A CTA covers exactly 256*U*E elements, no bounds checks anywhere; the (< one CTA) tail goes through
+// k_quantize_small on offset pointers.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int QT>
+__global__ void __launch_bounds__(256) k_quantize4_bulk(const T *__restrict__ A, float *__restrict__ absmax,
+                                                        unsigned char *__restrict__ out, int blocksize, int bs_shift) {
+  constexpr int E = 16 / sizeof(T);
+  constexpr int U = 4;
+  __shared__ __align__(16) QTables s_lut[1];
+  stage_tables<QT>(s_lut, nullptr, nullptr);
+
+  const int lane = threadIdx.x & 31;
+  const size_t v0 = ((size_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * (U * 32) + lane;
+  const int G = blocksize / E;
+  uint4 raw[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) raw[u] = ld_stream_u4(A + (v0 + u * 32) * E);
+
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const size_t e0 = (v0 + u * 32) * E;
+    const T *p = reinterpret_cast<const T *>(&raw[u]);
+    float x[E];
+    float m = 0.0f;   // == the reference's -FLT_MAX start for any block that holds a non-NaN value; a block of
+                      // NaNs only would give -FLT_MAX there and 0 here (both quantise every element to code 0)
+#pragma unroll
+    for (int j = 0; j < E; j++) { x[j] = to_float<T>(p[j]); m = fmaxf(m, fabsf(x[j])); }
+    for (int o = G >> 1; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((lane & (G - 1)) == 0) absmax[e0 >> bs_shift] = m;
+    const float inv = __fdiv_rn(1.0f, m);
+    uint32_t packed = 0;
+    if (inv < INFINITY) {
+#pragma unroll
+      for (int j = 0; j < E / 2; j++) {
+        const uint32_t hi = quantize4_lut<QT>(__fmul_rn(x[2 * j], inv), s_lut);
+        const uint32_t lo = quantize4_lut<QT>(__fmul_rn(x[2 * j + 1], inv), s_lut);
+        packed |= (hi * 16u + lo) << (8 * j);
+      }
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < E / 2; j++) {
+        const uint32_t hi = quantize4_tree<QT>(__fmul_rn(x[2 * j], inv));
+        const uint32_t lo = quantize4_tree<QT>(__fmul_rn(x[2 * j + 1], inv));
+        packed |= (hi * 16u + lo) << (8 * j);
+      }
+    }
+    if (E == 4) *reinterpret_cast<uint16_t *>(out + (e0 >> 1)) = (uint16_t)packed;
+    else *reinterpret_cast<uint32_t *>(out + (e0 >> 1)) = packed;
+  }
+}
+
 template <typename T, int QT>
 void quantize_blockwise(const float *code, const T *A, float *absmax, unsigned char *out, int blocksize, long n) {
   if (n <= 0) return;
@@ -278,6 +340,22 @@ void quantize_blockwise(const float *code, const T *A, float *absmax, unsigned c
   cudaStream_t st = current_stream();
   const bool aligned = (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 8 == 0);
   if (blocksize <= 32 * E) {
+    if (QT != General8bit && aligned) {
+      // bulk (whole CTAs, branch-free) + tail (generic kernel on offset pointers)
+      const long cta_elems = 256L * 4 * E;
+      const long nbulk = (n / cta_elems) * cta_elems;
+      int bs_shift = 0;
+      while ((1 << bs_shift) < blocksize) bs_shift++;
+      if (nbulk > 0)
+        k_quantize4_bulk<T, (QT == General8bit ? NF4 : QT)><<<(unsigned)(nbulk / cta_elems), 256, 0, st>>>(A, absmax, out, blocksize, bs_shift);
+      if (n > nbulk) {
+        const long rem = n - nbulk;
+        const unsigned grid = (unsigned)ceil_div_ll(ceil_div_ll(ceil_div_ll(rem, E), 32 * 4), 8);
+        k_quantize_small<T, QT, true><<<grid, 256, 0, st>>>(code, A + nbulk, absmax + nbulk / blocksize, out + nbulk / 2, blocksize, rem);
+      }
+      check_launch("quantize_blockwise");
+      return;
+    }
     const long nvec = ceil_div_ll(n, E);
     const long nwarps = ceil_div_ll(nvec, 32 * 4);
     const unsigned grid = (unsigned)ceil_div_ll(nwarps, 8);
