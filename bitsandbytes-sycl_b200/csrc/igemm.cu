@@ -44,7 +44,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 bool make_tmap_2d(CUtensorMap *map, const void *base, int elem_bytes, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                  uint32_t box_cols, bool is_16bit_float, bool is_bf16) {
+                  uint32_t box_cols, bool is_16bit_float, bool is_bf16, bool swizzle128) {
   auto fn = get_encode_fn();
   if (!fn) { latch_error(cudaErrorNotSupported, "cuTensorMapEncodeTiled unavailable"); return false; }
   CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_UINT8;
@@ -55,7 +55,8 @@ bool make_tmap_2d(CUtensorMap *map, const void *base, int elem_bytes, uint64_t r
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { latch_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled failed"); return false; }
   return true;
 }

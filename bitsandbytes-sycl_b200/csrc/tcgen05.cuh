@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace bnb {
 namespace tc {
@@ -114,6 +115,6 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 // host: build a 2-D tiled tensor map (row-major [rows, cols] of `elem_bytes` elements, box = box_cols x box_rows,
 // 128-byte swizzle).  Returns false (and latches an error) on failure.
 bool make_tmap_2d(CUtensorMap *map, const void *base, int elem_bytes, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                  uint32_t box_cols, bool is_bf16_or_f16, bool is_bf16);
+                  uint32_t box_cols, bool is_bf16_or_f16, bool is_bf16, bool swizzle128 = true);
 
 }  // namespace bnb
