@@ -27,6 +27,7 @@ void latch_error(cudaError_t e, const char *where) {
 template <typename T, int QT> void quantize_blockwise(const float *, const T *, float *, unsigned char *, int, long);
 template <typename T, int QT> void dequantize_blockwise(const float *, const unsigned char *, const float *, T *, int, long);
 long long selftest_quant_lut(int qtype);
+void gemv_probe(unsigned long long *out2);
 template <typename T> void gemv_4bit(int, int, int, const T *, const unsigned char *, const float *, const float *, T *, int, int, int, int);
 template <typename T> void gemv_4bit_nested(int, int, int, const T *, const unsigned char *, const unsigned char *, const float *, const float *, float, const float *, T *, int, int, int, int, int);
 template <typename T> int gemm_4bit(int, int, int, const T *, const unsigned char *, const float *, const float *, const T *, T *, int);
@@ -58,6 +59,7 @@ int cbnb_last_error(void) {
 const char *cbnb_last_error_string(void) { return tl_error_msg; }
 const char *cbnb_version(void) { return "bnb_b200 sm_100a r1"; }
 long long cbnb_selftest_quant_lut(int qtype) { return selftest_quant_lut(qtype); }
+void cbnb_debug_gemv_probe(unsigned long long *cycles_ns) { gemv_probe(cycles_ns); }
 
 // ---------------------------------------------------------------- blockwise quantize (pythonInterface.cpp:203-217)
 #define QUANT_FN(name, T, QT) \

@@ -38,6 +38,11 @@ __device__ __forceinline__ uint4 ld_stream_u4(const void *p) {
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
+// 256-bit variant (sm_100+): one lane fetches a whole 32-byte sector
+__device__ __forceinline__ void ld_stream_u8(uint32_t (&r)[8], const void *p) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
 __device__ __forceinline__ uint2 ld_stream_u2(const void *p) {
   uint2 r;
   asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));

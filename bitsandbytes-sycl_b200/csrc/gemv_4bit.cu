@@ -687,6 +687,240 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gemv4_tma(const GemvArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Block-column path (batch 1, blocksize 64, K % 256 == 0): the headline kernel.
+//
+// The MMA's eight output columns are not wasted on a single activation row: column j of the 16x8
+// accumulator collects the partial dot product of quantisation block j of a 512-element K chunk.  The k
+// slots of an MMA are spread over four blocks (lane t's slots <-> block t for "even" MMAs, block t + 4 for
+// "odd" ones), and the B fragment holds x only where its column equals the block of its k slots (lane
+// (g,t) feeds real activations to even MMAs iff g == t, to odd MMAs iff g == t + 4; every other lane feeds
+// zeros that are set once and never change).  One accumulator therefore
+// runs through all 32 MMAs of a (16-row tile, 512-K chunk) item, and afterwards every lane owns four
+// distinct (row, block) partial sums: the absmax scale -- and its de-nesting -- is applied ONCE per
+// (row, block) by exactly one lane (no 4x redundancy, no per-block accumulator reset).
+// Per item and lane: 32 x (4 PRMT + 4 LDS + 1 HMMA) + 8 LDG.128 (weights) + 16 one-wavefront LDS.128 (x)
+// + 4 de-nests = ~1.4 instructions per weight element, against ~3.3 for the per-block-accumulator kernels.
+//
+// A persistent CTA per SM owns a contiguous range of 16-row tiles; its 16 warps take (tile, chunk) items
+// round-robin, each warp keeps its weights in a register ring that is refilled half an item at a time
+// (3-4 KB per warp, ~56 KB per SM in flight towards HBM), partial sums of a tile meet in shared memory in a
+// fixed order (deterministic).
+// ------------------------------------------------------------------------------------------------
+constexpr int kBcXPitch = 144;                 // bytes per 64-element block of x in shared memory (128 + 16: conflict-free)
+constexpr int kBcHead = 1024 + 128;            // code2 | codeT
+constexpr int kBcSmemMax = 227 * 1024;
+
+__device__ __forceinline__ void lds_x4_pred(uint32_t (&b)[4], uint32_t saddr, uint32_t active) {
+  asm volatile("{\n .reg .pred P;\n setp.ne.u32 P, %5, 0;\n @P ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n}"
+               : "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]) : "r"(saddr), "r"(active));
+}
+
+// debug probe (flags bit 1): SM cycles and nanoseconds spent by CTA 0 -> effective SM clock under this kernel's load
+__device__ unsigned long long g_gemv_probe[2];
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+  return v;
+}
+
+template <typename T, bool NESTED, int EXP = 0, int DEPTH = 2, int WARPS = 16>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_gemv4_bc(const GemvArgs a, int x_blocks_padded, int tiles_total) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t lut_s = (smem_base + 0xFFFFu) & ~0xFFFFu;          // 64 KB-aligned shared address of the byte LUT
+  unsigned char *s_lut = smem + (lut_s - smem_base);
+  unsigned char *after = s_lut + 65536;
+  float *s_code2 = reinterpret_cast<float *>(after);
+  uint32_t *s_codeT = reinterpret_cast<uint32_t *>(after + 1024);
+  unsigned char *s_x = after + kBcHead;
+  float *s_part = reinterpret_cast<float *>(s_x + (size_t)x_blocks_padded * kBcXPitch);   // [tile_local][warp][16]
+  const uint32_t x_s = lut_s + 65536u + kBcHead;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  unsigned long long probe_c = 0, probe_t = 0;
+  if ((a.flags & 2) && blockIdx.x == 0 && tid == 0) { probe_c = clock64(); probe_t = globaltimer_ns(); }
+  const int kb = a.K >> 6;                 // blocks per row
+  const int nch = (a.K + 511) >> 9;        // 512-element chunks per row (the last one may be half)
+  const int row_bytes = a.K >> 1;
+  const int t_begin = (int)((long)blockIdx.x * tiles_total / gridDim.x);
+  const int t_end = (int)((long)(blockIdx.x + 1) * tiles_total / gridDim.x);
+  const int ntl = t_end - t_begin;
+
+  uint32_t w[DEPTH][2][2][8];   // [ring slot][block t / t+4][row half][32 bytes = one sector per lane]
+  struct Abs { uint32_t q[2]; float am2[2]; float2 am[2]; };
+  Abs ab[DEPTH];
+
+  // one 256-bit load per (row, block): a lane owns a whole 32-byte sector, 4 lanes one 128-byte line
+  auto load_w = [&](uint32_t (&dst)[2][8], int j, int tile, int c) {
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int row = min(tile * 16 + g + 8 * h, a.N - 1);
+      const unsigned char *p = a.B + (size_t)row * row_bytes + c * 256 + (t + 4 * j) * 32;
+      if (EXP == 2) {   // experiment: compute only, no global weight traffic
+#pragma unroll
+        for (int i = 0; i < 8; i++) dst[h][i] = (uint32_t)(tid * 2654435761u) + i * 0x01010101u + c;
+      } else if (c * 8 + t + 4 * j < kb) ld_stream_u8(dst[h], p);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) dst[h][i] = 0;
+      }
+    }
+  };
+  auto load_abs = [&](Abs &d, int tile, int c) {
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int row = min(tile * 16 + g + 8 * h, a.N - 1);
+      const size_t idx = (size_t)row * kb + min(c * 8 + 2 * t, kb - 2);
+      if (NESTED) {
+        d.q[h] = __ldg(reinterpret_cast<const unsigned short *>(a.qabsmax + idx));
+        d.am2[h] = __ldg(a.absmax2 + (idx >> a.bs2_shift));
+      } else {
+        d.am[h] = __ldg(reinterpret_cast<const float2 *>(a.absmax + idx));
+      }
+    }
+  };
+  auto advance = [&](int &tl_, int &c_) {
+    c_ += WARPS;
+    while (c_ >= nch) { c_ -= nch; tl_++; }
+  };
+
+  // compute cursor (tl, c) and load cursor (ltl, lc): the register ring keeps DEPTH items per warp in flight
+  int tl = 0, c = warp;
+  while (c >= nch) { c -= nch; tl++; }
+  int ltl = tl, lc = c;
+#pragma unroll
+  for (int s = 0; s < DEPTH; s++) {
+    if (ltl < ntl) {
+      load_w(w[s][0], 0, t_begin + ltl, lc);
+      load_w(w[s][1], 1, t_begin + ltl, lc);
+      load_abs(ab[s], t_begin + ltl, lc);
+    }
+    advance(ltl, lc);
+  }
+
+  // ---- prologue (overlaps the first loads): tables, activations, partial-sum slots
+  if (NESTED && tid < 256) s_code2[tid] = a.code2[tid];
+  if (tid < 16) s_codeT[tid] = MmaT<T>::pack(a.code[tid], 0.0f) & 0xFFFFu;
+  {
+    const uint4 *xg = reinterpret_cast<const uint4 *>(a.x);
+    const int pieces = x_blocks_padded * 8, valid = a.K >> 3;
+    for (int p0 = tid; p0 < pieces; p0 += 4 * (WARPS * 32)) {   // four independent loads in flight per thread
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int p = p0 + u * (WARPS * 32);
+        v[u] = p < valid ? __ldg(xg + p) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int p = p0 + u * (WARPS * 32);
+        if (p < pieces) *reinterpret_cast<uint4 *>(s_x + (p >> 3) * kBcXPitch + (p & 7) * 16) = v[u];
+      }
+    }
+    for (int i = tid; i < ntl * WARPS * 16; i += (WARPS * 32)) s_part[i] = 0.f;
+  }
+  __syncthreads();
+  {
+    const int j = tid & 7;
+#pragma unroll
+    for (int e = tid >> 3; e < 256; e += (WARPS * 32) / 8) {
+      const uint32_t v = s_codeT[e >> 4] | (s_codeT[e & 15] << 16);
+      *reinterpret_cast<uint4 *>(s_lut + e * 256 + j * 16) = make_uint4(v, v, v, v);
+    }
+  }
+  __syncthreads();
+
+  const uint32_t lutlane = lut_s | (uint32_t)(lane * 4);
+  const uint32_t act0 = (g == t), act1 = (g == t + 4);
+  const uint32_t xlane = x_s + g * kBcXPitch;
+  uint32_t b0[4] = {0, 0, 0, 0}, b1[4] = {0, 0, 0, 0};
+  float acc0 = 0.f, acc1 = 0.f;
+  const float offset = a.offset;
+
+  while (tl < ntl) {
+#pragma unroll
+    for (int s = 0; s < DEPTH; s++) {
+      if (tl >= ntl) break;
+      const bool lhave = ltl < ntl;
+      const uint32_t xc = xlane + c * (8 * kBcXPitch);
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 2; j++) {          // j = 0: blocks 0-3 (columns 0-3), j = 1: blocks 4-7 (columns 4-7)
+#pragma unroll
+        for (int mg = 0; mg < 8; mg++) {     // one 32-bit word of each row = 8 elements = 2 MMAs
+          if (EXP == 1) { d[0] += __uint_as_float((w[s][j][0][mg] ^ w[s][j][1][mg]) & 0x3fffffffu); continue; }  // experiment: stream only
+          if (j == 0) lds_x4_pred(b0, xc + mg * 16, act0);
+          else lds_x4_pred(b1, xc + mg * 16, act1);
+          const uint32_t s0 = w[s][j][0][mg], s1 = w[s][j][1][mg];
+#pragma unroll
+          for (int mm = 0; mm < 2; mm++) {
+            const uint32_t selA = 0x7604u | ((2 * mm) << 4), selB = 0x7604u | ((2 * mm + 1) << 4);
+            uint32_t af[4];
+            af[0] = lds_u32(__byte_perm(s0, lutlane, selA));
+            af[1] = lds_u32(__byte_perm(s1, lutlane, selA));
+            af[2] = lds_u32(__byte_perm(s0, lutlane, selB));
+            af[3] = lds_u32(__byte_perm(s1, lutlane, selB));
+            if (j == 0) MmaT<T>::mma(d, af, b0[2 * mm], b0[2 * mm + 1]);
+            else MmaT<T>::mma(d, af, b1[2 * mm], b1[2 * mm + 1]);
+          }
+        }
+        if (lhave) load_w(w[s][j], j, t_begin + ltl, lc);   // refill this half of the slot: item DEPTH ahead
+      }
+      float am00, am01, am10, am11;
+      if (NESTED) {
+        am00 = __fadd_rn(__fmul_rn(s_code2[ab[s].q[0] & 0xFFu], ab[s].am2[0]), offset);
+        am01 = __fadd_rn(__fmul_rn(s_code2[ab[s].q[0] >> 8], ab[s].am2[0]), offset);
+        am10 = __fadd_rn(__fmul_rn(s_code2[ab[s].q[1] & 0xFFu], ab[s].am2[1]), offset);
+        am11 = __fadd_rn(__fmul_rn(s_code2[ab[s].q[1] >> 8], ab[s].am2[1]), offset);
+      } else {
+        am00 = ab[s].am[0].x; am01 = ab[s].am[0].y; am10 = ab[s].am[1].x; am11 = ab[s].am[1].y;
+      }
+      if (lhave) load_abs(ab[s], t_begin + ltl, lc);
+      advance(ltl, lc);
+      acc0 = __fmaf_rn(d[0], am00, acc0);
+      acc0 = __fmaf_rn(d[1], am01, acc0);
+      acc1 = __fmaf_rn(d[2], am10, acc1);
+      acc1 = __fmaf_rn(d[3], am11, acc1);
+      int ntl_ = tl, nc = c;
+      advance(ntl_, nc);
+      if (ntl_ != tl) {   // this warp is done with the tile: park its partial sums
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+        if (t == 0) {
+          float *slot = s_part + (tl * WARPS + warp) * 16;
+          slot[g] = acc0;
+          slot[g + 8] = acc1;
+        }
+        acc0 = acc1 = 0.f;
+      }
+      tl = ntl_; c = nc;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < ntl * 16; i += (WARPS * 32)) {
+    const int tile_l = i >> 4, row = i & 15;
+    const float *p = s_part + tile_l * WARPS * 16 + row;
+    float sum = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < WARPS; wq++) sum += p[wq * 16];
+    const int r = (t_begin + tile_l) * 16 + row;
+    if (r < a.N) reinterpret_cast<T *>(a.out)[r] = from_float<T>(sum);
+  }
+  if ((a.flags & 2) && blockIdx.x == 0 && tid == 0) {
+    g_gemv_probe[0] = clock64() - probe_c;
+    g_gemv_probe[1] = globaltimer_ns() - probe_t;
+  }
+}
+
+// host: last probe of the block-column kernel -> {cycles, ns}
+void gemv_probe(unsigned long long *out2) {
+  cudaMemcpyFromSymbol(out2, g_gemv_probe, sizeof(unsigned long long) * 2);
+}
+
+// ------------------------------------------------------------------------------------------------
 // generic path: any K / ldb / blocksize / dtype (incl. fp32).  One warp per row, 16 packed bytes per
 // lane per step, fp32 math.  Semantics of the tail follow kernel_gemm.cpp:1312-1366: bytes at index
 // >= K/2 read as 0x77 and activations past K as 0.
@@ -745,6 +979,7 @@ static void launch_mma_inst(const GemvArgs &a) {
   if (exp_mode < 0) {
     const char *e = getenv("BNB_B200_GEMV_EXP"); exp_mode = e ? atoi(e) : 0;
     const char *f = getenv("BNB_B200_GEMV_PF"); pf_off = (f && f[0] == '0') ? 1 : 0;
+    const char *pr = getenv("BNB_B200_GEMV_PROBE"); if (pr && pr[0] == '1') pf_off |= 2;
   }
   GemvArgs a2 = a;
   a2.flags = pf_off;
@@ -755,8 +990,42 @@ static void launch_mma_inst(const GemvArgs &a) {
     cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
     attr_set[dev] = true;
   }
-  static int impl_reg = -1;
-  if (impl_reg < 0) { const char *e = getenv("BNB_B200_GEMV_IMPL"); impl_reg = (e && e[0] == 'r') ? 1 : 0; }
+  static int impl_reg = -1, impl_bc = 1;
+  if (impl_reg < 0) {
+    const char *e = getenv("BNB_B200_GEMV_IMPL");
+    impl_reg = (e && e[0] == 'r') ? 1 : 0;
+    impl_bc = (e && (e[0] == 'r' || e[0] == 't')) ? 0 : 1;
+  }
+  if (VEC4 && impl_bc && a.batch == 1) {
+    // block-column kernel: shared memory = 64 KB alignment slack + LUT + head + x (144 B per block) + partial sums
+    static int cfg = -1;   // experiment knob: BNB_B200_GEMV_CFG = <depth><warps/4>, e.g. 24 = depth 2, 16 warps
+    if (cfg < 0) { const char *e = getenv("BNB_B200_GEMV_CFG"); cfg = e ? atoi(e) : 24; }
+    const int warps = (cfg % 10) * 4;
+    const int tiles = ceil_div(a.N, 16);
+    const int grid = tiles < num_sms[dev] ? tiles : num_sms[dev];
+    const int xblocks = ceil_div(a.K, 512) * 8;
+    const int ntl_max = ceil_div(tiles, grid);
+    const size_t need = 65536 + 65536 + kBcHead + (size_t)xblocks * kBcXPitch + (size_t)ntl_max * warps * 16 * sizeof(float);
+    if (need <= (size_t)kBcSmemMax) {
+#define BC_LAUNCH(EXP_, DEPTH_, WARPS_)                                                                                  \
+  do {                                                                                                                  \
+    auto kfn = k_gemv4_bc<T, NESTED, EXP_, DEPTH_, WARPS_>;                                                             \
+    latch_error(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kBcSmemMax), "gemv bc smem attr"); \
+    kfn<<<grid, WARPS_ * 32, need, current_stream()>>>(a2, xblocks, tiles);                                             \
+  } while (0)
+      if (exp_mode == 1) BC_LAUNCH(1, 2, 16);
+      else if (exp_mode == 2 && cfg == 15) BC_LAUNCH(2, 1, 20);
+      else if (exp_mode == 2 && cfg == 16) BC_LAUNCH(2, 1, 24);
+      else if (exp_mode == 2) BC_LAUNCH(2, 2, 16);
+      else if (cfg == 14) BC_LAUNCH(0, 1, 16);
+      else if (cfg == 15) BC_LAUNCH(0, 1, 20);
+      else if (cfg == 16) BC_LAUNCH(0, 1, 24);
+      else BC_LAUNCH(0, 2, 16);
+#undef BC_LAUNCH
+      check_launch("gemv_4bit (block-column)");
+      return;
+    }
+  }
   if (VEC4 && !impl_reg && exp_mode == 0) {
     static bool attr2[64] = {false};
     if (!attr2[dev]) {

@@ -116,6 +116,10 @@ BNB_B200_API const char *cbnb_version(void);
  * 4-bit quantiser disagrees with the reference decision tree; qtype 1 = FP4, 2 = NF4. Must return 0. */
 BNB_B200_API long long cbnb_selftest_quant_lut(int qtype);
 
+/* debug: {SM cycles, nanoseconds} CTA 0 of the last block-column GEMV spent (recorded only when the
+ * environment has BNB_B200_GEMV_PROBE=1) -> effective SM clock under the kernel's own load */
+BNB_B200_API void cbnb_debug_gemv_probe(unsigned long long *cycles_ns);
+
 /* GEMV with the NESTED (double-quantised) absmax consumed directly: qabsmax uint8 [N*K/blocksize],
  * absmax2 fp32 [ceil(nblocks/blocksize2)], code2 fp32[256], offset scalar. De-nesting is
  * fl(fl(code2[q] * absmax2[i / blocksize2]) + offset), identical to functional.py:1982-1984. */

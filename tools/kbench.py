@@ -113,7 +113,14 @@ def bench_gemv(iters, shapes=None, dtypes=(torch.bfloat16,)):
             outs = [torch.empty(1, N, dtype=dt, device="cuda") for _ in range(nbuf)]
             fns = [(lambda i=i: F.gemv_4bit(x, packs[i].t(), out=outs[i], state=st)) for i in range(nbuf)]
             us = time_graph(fns, iters)
-            report(f"gemv_nf4_nested_{str(dt).split('.')[-1]}_{N}x{K}", us, gemv_bytes(N, K), buffers=nbuf)
+            extra = {}
+            if os.environ.get("BNB_B200_GEMV_PROBE") == "1":
+                import ctypes as ct
+                buf = (ct.c_ulonglong * 2)()
+                F.lib.cbnb_debug_gemv_probe(buf)
+                if buf[1]:
+                    extra = {"cta0_us": round(buf[1] / 1e3, 2), "sm_mhz_in_kernel": round(buf[0] * 1e3 / buf[1], 1)}
+            report(f"gemv_nf4_nested_{str(dt).split('.')[-1]}_{N}x{K}", us, gemv_bytes(N, K), buffers=nbuf, **extra)
             del packs, outs
             torch.cuda.empty_cache()
 
