@@ -21,6 +21,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace bnb {
 
@@ -234,6 +235,12 @@ template <bool NESTED> struct FastBuf {
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+
+__device__ __forceinline__ uint4 lds_u128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
   return v;
 }
 
@@ -915,6 +922,238 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_gemv4_bc(const GemvArgs a, in
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA-staged block-column kernel (the production path for batch 1).
+//
+// Same arithmetic as k_gemv4_bc, different data movement.  Global loads issued by the compute warps share the
+// LSU / L1TEX pipe with the LUT lookups, and that pipe -- not HBM, not issue slots -- is what bounds this kernel
+// (measured: stream-only and compute-only each run at ~5.5 TB/s-equivalent, together at 3.4).  So the packed
+// weights never touch L1TEX: they are streamed by TMA (cp.async.bulk.tensor, two 16-row x 128-byte boxes per
+// item, 128-byte swizzle, out-of-bounds rows / columns zero-filled by the hardware) into a shared-memory ring
+// of `nslots` 4 KB slots, completion on one mbarrier per slot.  Item i of the CTA lives in slot i % nslots and
+// is consumed by warp i % WARPS: the warp waits for the slot, lifts its 4 KB into registers with eight
+// conflict-free LDS.128 and immediately re-arms the slot with the TMA loads of item i + nslots -- the consumer
+// of a slot is the producer of its next use (nslots is a multiple of WARPS, so a slot always belongs to the same
+// warp and its mbarrier phases are ordered by that warp's program order): there is no producer warp to fall
+// behind and no "empty" barrier.  The ring depth, not the register file, sets the bytes in flight towards HBM.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBctSlot = 4096;                     // one item: 2 boxes of 16 rows x 128 B
+constexpr int kBctLut = 0;                         // [0, 64 KB): byte LUT, entry stride 256 B
+constexpr int kBctBars = 65536;                    // full[nslots] (8 B each), codeT
+constexpr int kBctCode2 = 65536 + 1024;
+constexpr int kBctRing = 65536 + 2048;             // 1024-byte aligned slots
+constexpr int kBctMaxSlots = 64;
+
+template <typename T, bool NESTED, int WARPS, int EXP = 0>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_gemv4_bct(const GemvArgs a, const __grid_constant__ CUtensorMap tmapB, int x_blocks_padded, int tiles_total, int nslots) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // 128-byte-swizzled TMA destinations need 1024-byte alignment: align by hand (the launch adds 1 KB of slack)
+  const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  unsigned char *smem = smem_raw + (((raw_s + 1023u) & ~1023u) - raw_s);
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+  uint32_t *s_codeT = reinterpret_cast<uint32_t *>(smem + kBctBars + kBctMaxSlots * 8);
+  float *s_code2 = reinterpret_cast<float *>(smem + kBctCode2);
+  unsigned char *s_x = smem + kBctRing + nslots * kBctSlot;
+  float *s_part = reinterpret_cast<float *>(s_x + (size_t)x_blocks_padded * kBcXPitch);   // [tile_local][warp][16]
+  const uint32_t full_s = smem_base + kBctBars;
+  const uint32_t ring_s = smem_base + kBctRing;
+  constexpr int CT = WARPS * 32;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned long long probe_c = 0, probe_t = 0;
+  if ((a.flags & 2) && blockIdx.x == 0 && tid == 0) { probe_c = clock64(); probe_t = globaltimer_ns(); }
+  const int kb = a.K >> 6;
+  const int nch = (a.K + 511) >> 9;
+  const int t_begin = (int)((long)blockIdx.x * tiles_total / gridDim.x);
+  const int t_end = (int)((long)(blockIdx.x + 1) * tiles_total / gridDim.x);
+  const int ntl = t_end - t_begin;
+  const int nitems = ntl * nch;
+
+  if (tid == 0) {
+    tc::prefetch_tmap(&tmapB);
+    for (int i = 0; i < nslots; i++) tc::mbar_init(full_s + i * 8, 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int slot, int tl_, int c_) {   // one lane: arm the slot's barrier and start its two boxes
+    const uint32_t bar = full_s + slot * 8, dst = ring_s + slot * kBctSlot;
+    tc::mbar_arrive_expect_tx(bar, kBctSlot);
+    tc::tma_load_2d(dst, &tmapB, bar, c_ * 256, (t_begin + tl_) * 16);
+    tc::tma_load_2d(dst + 2048, &tmapB, bar, c_ * 256 + 128, (t_begin + tl_) * 16);
+  };
+  // first fill of the ring: item i (< nslots) is started by the warp that will consume it or one of its peers
+  if (lane == 0) {
+    for (int i = warp; i < nslots && i < nitems; i += WARPS) issue(i, i / nch, i % nch);
+  }
+
+  // ---- prologue (overlaps the first TMA loads): tables, activations, partial-sum slots
+  if (NESTED && tid < 256) s_code2[tid] = a.code2[tid];
+  if (tid < 16) s_codeT[tid] = MmaT<T>::pack(a.code[tid], 0.0f) & 0xFFFFu;
+  {
+    const uint4 *xg = reinterpret_cast<const uint4 *>(a.x);
+    const int pieces = x_blocks_padded * 8, valid = a.K >> 3;
+    for (int p0 = tid; p0 < pieces; p0 += 4 * CT) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int p = p0 + u * CT;
+        v[u] = p < valid ? __ldg(xg + p) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int p = p0 + u * CT;
+        if (p < pieces) *reinterpret_cast<uint4 *>(s_x + (p >> 3) * kBcXPitch + (p & 7) * 16) = v[u];
+      }
+    }
+    for (int i = tid; i < ntl * WARPS * 16; i += CT) s_part[i] = 0.f;
+  }
+  __syncthreads();
+  {
+    const int j = tid & 7;
+    for (int e = tid >> 3; e < 256; e += CT / 8) {
+      const uint32_t v = s_codeT[e >> 4] | (s_codeT[e & 15] << 16);
+      *reinterpret_cast<uint4 *>(smem + kBctLut + e * 256 + j * 16) = make_uint4(v, v, v, v);
+    }
+  }
+  __syncthreads();
+
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t lane4 = (uint32_t)(lane * 4);
+  const uint32_t act0 = (g == t), act1 = (g == t + 4);
+  const uint32_t xlane = smem_base + (uint32_t)(kBctRing + nslots * kBctSlot) + g * kBcXPitch;
+  // this lane's two 16-byte pieces (q = 0, 1) of block t inside a swizzled 128-byte row: chunk (2t+q) ^ (row & 7)
+  const uint32_t wl0 = (uint32_t)(g * 128 + (((2 * t) ^ (g & 7)) << 4));
+  const uint32_t wl1 = (uint32_t)(g * 128 + (((2 * t + 1) ^ (g & 7)) << 4));
+  uint32_t b0[4] = {0, 0, 0, 0}, b1[4] = {0, 0, 0, 0};
+  float acc0 = 0.f, acc1 = 0.f;
+  const float offset = a.offset;
+  struct Abs { uint32_t q[2]; float am2[2]; float2 am[2]; };
+  auto load_abs = [&](Abs &d, int tile, int c) {
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int row = min(tile * 16 + g + 8 * h, a.N - 1);
+      const size_t idx = (size_t)row * kb + min(c * 8 + 2 * t, kb - 2);
+      if (NESTED) {
+        d.q[h] = __ldg(reinterpret_cast<const unsigned short *>(a.qabsmax + idx));
+        d.am2[h] = __ldg(a.absmax2 + (idx >> a.bs2_shift));
+      } else {
+        d.am[h] = __ldg(reinterpret_cast<const float2 *>(a.absmax + idx));
+      }
+    }
+  };
+  auto advance = [&](int &tl_, int &c_, int by) {
+    c_ += by;
+    while (c_ >= nch) { c_ -= nch; tl_++; }
+  };
+
+  int tl = 0, c = 0;                 // compute cursor: item `warp`
+  advance(tl, c, warp);
+  int itl = tl, ic = c;              // issue cursor: compute cursor + nslots items
+  advance(itl, ic, nslots);
+  int slot = warp % nslots;
+  uint32_t parity = (uint32_t)(warp / nslots) & 1u;
+  Abs cur, nxt;
+  if (tl < ntl) load_abs(cur, t_begin + tl, c);
+  for (int i = warp; i < nitems; i += WARPS) {
+    int ntl_ = tl, nc = c;
+    advance(ntl_, nc, WARPS);
+    if (ntl_ < ntl) load_abs(nxt, t_begin + ntl_, nc);
+    const uint32_t slot_s = ring_s + slot * kBctSlot;
+    if (EXP != 2 || i < nslots) tc::mbar_wait(full_s + slot * 8, parity);   // EXP 2: compute only, ring filled once
+    uint4 w[2][2][2];   // [block half j][row half h][q]
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        w[j][h][0] = lds_u128(slot_s + j * 2048 + h * 1024 + wl0);
+        w[j][h][1] = lds_u128(slot_s + j * 2048 + h * 1024 + wl1);
+      }
+    // the slot is free once every lane holds its bytes: wait for the loads (register dependency), then re-arm it
+    asm volatile("" ::"r"(w[0][0][0].x), "r"(w[0][1][0].x), "r"(w[1][0][0].x), "r"(w[1][1][0].x), "r"(w[0][0][1].x), "r"(w[0][1][1].x), "r"(w[1][0][1].x), "r"(w[1][1][1].x) : "memory");
+    __syncwarp();
+    if (EXP != 2 && lane == 0 && itl < ntl) {
+      tc::fence_proxy_async();        // generic-proxy reads of the slot before the async-proxy (TMA) overwrite
+      issue(slot, itl, ic);
+    }
+    advance(itl, ic, WARPS);
+    slot += WARPS;
+    while (slot >= nslots) { slot -= nslots; parity ^= 1u; }
+
+    const uint32_t xc = xlane + c * (8 * kBcXPitch);
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+#pragma unroll
+      for (int mg = 0; mg < 8; mg++) {
+        if (EXP == 1) {   // experiment: stream only
+          d[0] += __uint_as_float((w[j][0][mg >> 2].x ^ w[j][1][mg >> 2].y ^ w[j][0][mg >> 2].z ^ w[j][1][mg >> 2].w) & 0x3fffffffu);
+          continue;
+        }
+        if (j == 0) lds_x4_pred(b0, xc + mg * 16, act0);
+        else lds_x4_pred(b1, xc + mg * 16, act1);
+        const uint4 &v0 = w[j][0][mg >> 2], &v1 = w[j][1][mg >> 2];
+        const int wi = mg & 3;
+        const uint32_t s0 = wi == 0 ? v0.x : wi == 1 ? v0.y : wi == 2 ? v0.z : v0.w;
+        const uint32_t s1 = wi == 0 ? v1.x : wi == 1 ? v1.y : wi == 2 ? v1.z : v1.w;
+#pragma unroll
+        for (int mm = 0; mm < 2; mm++) {
+          // offset = byte * 256 + lane * 4 (one PRMT); the LUT base is a compile-time offset of the shared window
+          const uint32_t selA = 0x7604u | ((2 * mm) << 4), selB = 0x7604u | ((2 * mm + 1) << 4);
+          uint32_t af[4];
+          af[0] = *reinterpret_cast<const uint32_t *>(smem + kBctLut + __byte_perm(s0, lane4, selA));
+          af[1] = *reinterpret_cast<const uint32_t *>(smem + kBctLut + __byte_perm(s1, lane4, selA));
+          af[2] = *reinterpret_cast<const uint32_t *>(smem + kBctLut + __byte_perm(s0, lane4, selB));
+          af[3] = *reinterpret_cast<const uint32_t *>(smem + kBctLut + __byte_perm(s1, lane4, selB));
+          if (j == 0) MmaT<T>::mma(d, af, b0[2 * mm], b0[2 * mm + 1]);
+          else MmaT<T>::mma(d, af, b1[2 * mm], b1[2 * mm + 1]);
+        }
+      }
+    }
+    float am00, am01, am10, am11;
+    if (NESTED) {
+      am00 = __fadd_rn(__fmul_rn(s_code2[cur.q[0] & 0xFFu], cur.am2[0]), offset);
+      am01 = __fadd_rn(__fmul_rn(s_code2[cur.q[0] >> 8], cur.am2[0]), offset);
+      am10 = __fadd_rn(__fmul_rn(s_code2[cur.q[1] & 0xFFu], cur.am2[1]), offset);
+      am11 = __fadd_rn(__fmul_rn(s_code2[cur.q[1] >> 8], cur.am2[1]), offset);
+    } else {
+      am00 = cur.am[0].x; am01 = cur.am[0].y; am10 = cur.am[1].x; am11 = cur.am[1].y;
+    }
+    acc0 = __fmaf_rn(d[0], am00, acc0);
+    acc0 = __fmaf_rn(d[1], am01, acc0);
+    acc1 = __fmaf_rn(d[2], am10, acc1);
+    acc1 = __fmaf_rn(d[3], am11, acc1);
+    if (ntl_ != tl) {   // this warp is done with the tile: park its partial sums
+      acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
+      acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
+      acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
+      acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+      if (t == 0) {
+        float *slot_p = s_part + (tl * WARPS + warp) * 16;
+        slot_p[g] = acc0;
+        slot_p[g + 8] = acc1;
+      }
+      acc0 = acc1 = 0.f;
+    }
+    tl = ntl_; c = nc; cur = nxt;
+  }
+  __syncthreads();
+  for (int i = tid; i < ntl * 16; i += CT) {
+    const int tile_l = i >> 4, row = i & 15;
+    const float *p = s_part + tile_l * WARPS * 16 + row;
+    float sum = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < WARPS; wq++) sum += p[wq * 16];
+    const int r = (t_begin + tile_l) * 16 + row;
+    if (r < a.N) reinterpret_cast<T *>(a.out)[r] = from_float<T>(sum);
+  }
+  if ((a.flags & 2) && blockIdx.x == 0 && tid == 0) {
+    g_gemv_probe[0] = clock64() - probe_c;
+    g_gemv_probe[1] = globaltimer_ns() - probe_t;
+  }
+}
+
 // host: last probe of the block-column kernel -> {cycles, ns}
 void gemv_probe(unsigned long long *out2) {
   cudaMemcpyFromSymbol(out2, g_gemv_probe, sizeof(unsigned long long) * 2);
@@ -996,10 +1235,45 @@ static void launch_mma_inst(const GemvArgs &a) {
     impl_reg = (e && e[0] == 'r') ? 1 : 0;
     impl_bc = (e && (e[0] == 'r' || e[0] == 't')) ? 0 : 1;
   }
+  static int cfg_t = -1;   // experiment knob: BNB_B200_GEMV_CFG = <impl><warps/4>: 3x = TMA ring, 1x/2x = register ring depth 1/2
+  if (cfg_t < 0) { const char *e = getenv("BNB_B200_GEMV_CFG"); cfg_t = e ? atoi(e) : 34; }
+  if (VEC4 && impl_bc && a.batch == 1 && cfg_t >= 30) {
+    const int warps = (cfg_t % 10) * 4;
+    const int tiles = ceil_div(a.N, 16);
+    const int grid = tiles < num_sms[dev] ? tiles : num_sms[dev];
+    const int xblocks = ceil_div(a.K, 512) * 8;
+    const int ntl_max = ceil_div(tiles, grid);
+    const size_t fixed = 1024 + kBctRing + (size_t)xblocks * kBcXPitch + (size_t)ntl_max * warps * 16 * sizeof(float);
+    int nslots = fixed < (size_t)kBcSmemMax ? (int)(((size_t)kBcSmemMax - fixed) / kBctSlot) : 0;
+    if (nslots > kBctMaxSlots) nslots = kBctMaxSlots;
+    const int items_max = ntl_max * ceil_div(a.K, 512);
+    (void)items_max;
+    { static int cap = -1; if (cap < 0) { const char *e = getenv("BNB_B200_GEMV_SLOTS"); cap = e ? atoi(e) : 0; } if (cap > 0 && nslots > cap) nslots = cap; }
+    // a slot must always be consumed (and re-armed) by the same warp -- that is what orders its mbarrier phases
+    // without an "empty" barrier -- so the ring holds a whole number of items per warp
+    nslots = (nslots / warps) * warps;
+    CUtensorMap tmap;
+    if (nslots >= warps && make_tmap_2d(&tmap, a.B, 1, (uint64_t)a.N, (uint64_t)(a.K / 2), 16, 128, false, false, true)) {
+      const size_t need = fixed + (size_t)nslots * kBctSlot;
+#define BCT_LAUNCH(WARPS_)                                                                                               \
+  do {                                                                                                                  \
+    auto kfn = exp_mode == 1 ? k_gemv4_bct<T, NESTED, WARPS_, 1> : exp_mode == 2 ? k_gemv4_bct<T, NESTED, WARPS_, 2> : k_gemv4_bct<T, NESTED, WARPS_, 0>;                                                                       \
+    latch_error(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kBcSmemMax), "gemv bct smem attr"); \
+    kfn<<<grid, WARPS_ * 32, need, current_stream()>>>(a2, tmap, xblocks, tiles, nslots);                         \
+  } while (0)
+      if (warps == 20) BCT_LAUNCH(20);
+      else if (warps == 24) BCT_LAUNCH(24);
+      else if (warps == 12) BCT_LAUNCH(12);
+      else BCT_LAUNCH(16);
+#undef BCT_LAUNCH
+      check_launch("gemv_4bit (TMA block-column)");
+      return;
+    }
+  }
   if (VEC4 && impl_bc && a.batch == 1) {
     // block-column kernel: shared memory = 64 KB alignment slack + LUT + head + x (144 B per block) + partial sums
     static int cfg = -1;   // experiment knob: BNB_B200_GEMV_CFG = <depth><warps/4>, e.g. 24 = depth 2, 16 warps
-    if (cfg < 0) { const char *e = getenv("BNB_B200_GEMV_CFG"); cfg = e ? atoi(e) : 24; }
+    if (cfg < 0) { const char *e = getenv("BNB_B200_GEMV_CFG"); cfg = e ? atoi(e) : 24; if (cfg >= 30) cfg = 24; }
     const int warps = (cfg % 10) * 4;
     const int tiles = ceil_div(a.N, 16);
     const int grid = tiles < num_sms[dev] ? tiles : num_sms[dev];
