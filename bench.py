@@ -15,7 +15,7 @@ value      = algorithmic bytes of the whole job / device time (CUDA events, max 
 e2e        = same metric through the public API (bnb_b200.matmul_4bit, what Linear4bit.forward calls) with
              the step's activations copied from pinned host memory and the outputs copied back, all
              inside the timed region.
-roofline   = dominant kernel (k_gemv4_mma<bf16, nested>): algorithmic bytes per launch / average launch
+roofline   = dominant kernel (k_gemv4_bc<bf16, nested>): algorithmic bytes per launch / average launch
              duration measured with CUDA events on the launch stream over the timed region; peak =
              MEASURED_PEAKS.json hbm_gbs (else the profiling guide's 6650 GB/s fallback).
 cpu_baseline / --impl reference = the reference's own CPU path for this metric (BASELINE.json):
@@ -59,35 +59,66 @@ def measured_peak_gbs():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML through pynvml
+    (sub-millisecond queries, the timed region lasts tens of ms); falls back to polling nvidia-smi."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.samples = []      # (sm_mhz, reasons bitmask or list)
+        self.max_mhz = None
         self.stop_flag = threading.Event()
+        self.timed = threading.Event()   # set while the timed region runs: only those samples count
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        if self.nvml is not None:
+            n = self.nvml
+            names = [("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown if hasattr(n, "nvmlClocksEventReasonHwSlowdown") else 0x8),
+                     ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+            while not self.stop_flag.is_set():
+                try:
+                    mhz = int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                    try:
+                        mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    except Exception:
+                        mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    if self.timed.is_set():
+                        self.samples.append((mhz, [k for k, bit in names if mask & bit]))
+                except Exception:
+                    pass
+                self.stop_flag.wait(0.001)
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                f = [x.strip() for x in out.split(",")]
+                if len(f) >= 6 and f[0].isdigit():
+                    self.max_mhz = int(f[1]) if f[1].isdigit() else self.max_mhz
+                    self.samples.append((int(f[0]), [nm for i, nm in enumerate(names) if f[2 + i].lower().startswith("active")]))
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.05)
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples if len(s) >= 6)]
-        mx = next((int(s[1]) for s in self.samples if s[1].isdigit()), None)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.samples)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = sorted({r for s in self.samples for r in s[1]})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.samples),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -166,10 +197,10 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--layers", type=int, default=4)
+    ap.add_argument("--layers", type=int, default=32, help="decoder layers in the stack (32 = the whole Llama-2-7B)")
     ap.add_argument("--workload", default="llama2-7b", choices=["llama2-7b", "llama3-70b"])
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -308,8 +339,16 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.timed.set()
     ms_total = timed(step_kernel_only, args.steps, args.warmup)
+    # the timed region lasts tens of ms: keep the same load running ~0.3 s longer so the clock record has enough
+    # samples of the GPU under exactly this load (these extra steps are not part of any number; every rank runs
+    # the same count, ms_total being the max over ranks)
+    for _ in range(min(2000, max(1, int(300.0 / max(ms_total / args.steps, 1e-3))))):
+        step_kernel_only()
+    torch.cuda.synchronize()
     if rank == 0:
+        sampler.timed.clear()
         sampler.stop_flag.set()
     # e2e: host timer around the same loop (copies + API calls + sync are inside)
     for _ in range(2):
@@ -344,7 +383,7 @@ def main():
                        "launch": "cuda-graph" if graphed else "eager",
                        "parallelism": f"n-shard{world}+allgather" if world > 1 else "single"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_gemv4_mma<bf16,nested>", "peak_source": peak_kind,
+                         "traffic": None, "kernel": "k_gemv4_bc<bf16,nested>", "peak_source": peak_kind,
                          "bytes_per_launch": bytes_per_launch, "launch_us": launch_ms * 1e3},
             "e2e": {"value": alg_bytes / (e2e_s / e2e_steps) / 1e9, "unit": "GB/s",
                     "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": y_host.numel() * 2,

@@ -717,6 +717,12 @@ constexpr int kBcXPitch = 144;                 // bytes per 64-element block of 
 constexpr int kBcHead = 1024 + 128;            // code2 | codeT
 constexpr int kBcSmemMax = 227 * 1024;
 
+// activations may have been produced by the kernel just before this one (PDL): coherent load, not .nc
+__device__ __forceinline__ uint4 ld_x_u4(const uint4 *p) {
+  uint4 r;
+  asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
 __device__ __forceinline__ void lds_x4_pred(uint32_t (&b)[4], uint32_t saddr, uint32_t active) {
   asm volatile("{\n .reg .pred P;\n setp.ne.u32 P, %5, 0;\n @P ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n}"
                : "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]) : "r"(saddr), "r"(active));
@@ -731,17 +737,18 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 template <typename T, bool NESTED, int EXP = 0, int DEPTH = 2, int WARPS = 16>
-__global__ void __launch_bounds__(WARPS * 32, 1) k_gemv4_bc(const GemvArgs a, int x_blocks_padded, int tiles_total) {
+__global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(const GemvArgs a, int x_blocks_padded, int tiles_total) {
+  // shared memory: [0, 64 KB) byte LUT (entry stride 256 B, one word per lane) | code2 | x | partial sums.
+  // The lookup address is  LUT base (uniform register) + PRMT(byte << 8 | lane * 4): no alignment requirement.
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
-  const uint32_t lut_s = (smem_base + 0xFFFFu) & ~0xFFFFu;          // 64 KB-aligned shared address of the byte LUT
-  unsigned char *s_lut = smem + (lut_s - smem_base);
-  unsigned char *after = s_lut + 65536;
-  float *s_code2 = reinterpret_cast<float *>(after);
-  uint32_t *s_codeT = reinterpret_cast<uint32_t *>(after + 1024);
-  unsigned char *s_x = after + kBcHead;
+  float *s_code2 = reinterpret_cast<float *>(smem + 65536);
+  unsigned char *s_x = smem + 65536 + kBcHead;
   float *s_part = reinterpret_cast<float *>(s_x + (size_t)x_blocks_padded * kBcXPitch);   // [tile_local][warp][16]
-  const uint32_t x_s = lut_s + 65536u + kBcHead;
+  const uint32_t x_s = smem_base + 65536u + kBcHead;
+  // programmatic dependent launch: let the next kernel of the stream start its own prologue (tables, first
+  // weight loads) while this one is still running; it waits (griddepcontrol.wait) before touching x / out
+  asm volatile("griddepcontrol.launch_dependents;");
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -806,39 +813,39 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_gemv4_bc(const GemvArgs a, in
     advance(ltl, lc);
   }
 
-  // ---- prologue (overlaps the first loads): tables, activations, partial-sum slots
-  if (NESTED && tid < 256) s_code2[tid] = a.code2[tid];
-  if (tid < 16) s_codeT[tid] = MmaT<T>::pack(a.code[tid], 0.0f) & 0xFFFFu;
+  // ---- prologue (overlaps the first weight loads): tables and partial-sum slots; everything here reads only
+  // constants (code, code2), so it may run before the previous kernel of the stream has finished
   {
+    constexpr int CT = WARPS * 32;
+    for (int i = tid; i < 256; i += CT) if (NESTED) s_code2[i] = __ldg(a.code2 + i);
+    // byte e -> {T(code[e >> 4]), T(code[e & 15])}, replicated for the 32 lanes (bank == lane): 8 threads write
+    // one 128-byte entry with conflict-free 128-bit stores
+    const int j = tid & 7;
+    for (int e = tid >> 3; e < 256; e += CT / 8) {
+      const uint32_t v = (MmaT<T>::pack(__ldg(a.code + (e >> 4)), 0.0f) & 0xFFFFu) | (MmaT<T>::pack(__ldg(a.code + (e & 15)), 0.0f) << 16);
+      *reinterpret_cast<uint4 *>(smem + e * 256 + j * 16) = make_uint4(v, v, v, v);
+    }
+    for (int i = tid; i < ntl * WARPS * 16; i += CT) s_part[i] = 0.f;
+    asm volatile("griddepcontrol.wait;" ::: "memory");     // x (and out) belong to the previous kernel until here
     const uint4 *xg = reinterpret_cast<const uint4 *>(a.x);
     const int pieces = x_blocks_padded * 8, valid = a.K >> 3;
-    for (int p0 = tid; p0 < pieces; p0 += 4 * (WARPS * 32)) {   // four independent loads in flight per thread
+    for (int p0 = tid; p0 < pieces; p0 += 4 * CT) {   // four independent loads in flight per thread
       uint4 v[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        const int p = p0 + u * (WARPS * 32);
-        v[u] = p < valid ? __ldg(xg + p) : make_uint4(0, 0, 0, 0);
+        const int p = p0 + u * CT;
+        v[u] = p < valid ? ld_x_u4(xg + p) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        const int p = p0 + u * (WARPS * 32);
+        const int p = p0 + u * CT;
         if (p < pieces) *reinterpret_cast<uint4 *>(s_x + (p >> 3) * kBcXPitch + (p & 7) * 16) = v[u];
       }
-    }
-    for (int i = tid; i < ntl * WARPS * 16; i += (WARPS * 32)) s_part[i] = 0.f;
-  }
-  __syncthreads();
-  {
-    const int j = tid & 7;
-#pragma unroll
-    for (int e = tid >> 3; e < 256; e += (WARPS * 32) / 8) {
-      const uint32_t v = s_codeT[e >> 4] | (s_codeT[e & 15] << 16);
-      *reinterpret_cast<uint4 *>(s_lut + e * 256 + j * 16) = make_uint4(v, v, v, v);
     }
   }
   __syncthreads();
 
-  const uint32_t lutlane = lut_s | (uint32_t)(lane * 4);
+  const uint32_t lane4 = (uint32_t)(lane * 4);
   const uint32_t act0 = (g == t), act1 = (g == t + 4);
   const uint32_t xlane = x_s + g * kBcXPitch;
   uint32_t b0[4] = {0, 0, 0, 0}, b1[4] = {0, 0, 0, 0};
@@ -864,10 +871,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_gemv4_bc(const GemvArgs a, in
           for (int mm = 0; mm < 2; mm++) {
             const uint32_t selA = 0x7604u | ((2 * mm) << 4), selB = 0x7604u | ((2 * mm + 1) << 4);
             uint32_t af[4];
-            af[0] = lds_u32(__byte_perm(s0, lutlane, selA));
-            af[1] = lds_u32(__byte_perm(s1, lutlane, selA));
-            af[2] = lds_u32(__byte_perm(s0, lutlane, selB));
-            af[3] = lds_u32(__byte_perm(s1, lutlane, selB));
+            af[0] = *reinterpret_cast<const uint32_t *>(smem + __byte_perm(s0, lane4, selA));
+            af[1] = *reinterpret_cast<const uint32_t *>(smem + __byte_perm(s1, lane4, selA));
+            af[2] = *reinterpret_cast<const uint32_t *>(smem + __byte_perm(s0, lane4, selB));
+            af[3] = *reinterpret_cast<const uint32_t *>(smem + __byte_perm(s1, lane4, selB));
             if (j == 0) MmaT<T>::mma(d, af, b0[2 * mm], b0[2 * mm + 1]);
             else MmaT<T>::mma(d, af, b1[2 * mm], b1[2 * mm + 1]);
           }
@@ -1235,8 +1242,10 @@ static void launch_mma_inst(const GemvArgs &a) {
     impl_reg = (e && e[0] == 'r') ? 1 : 0;
     impl_bc = (e && (e[0] == 'r' || e[0] == 't')) ? 0 : 1;
   }
+  static int pdl_off = -1;
+  if (pdl_off < 0) { const char *e = getenv("BNB_B200_GEMV_PDL"); pdl_off = (e && e[0] == '0') ? 1 : 0; }
   static int cfg_t = -1;   // experiment knob: BNB_B200_GEMV_CFG = <impl><warps/4>: 3x = TMA ring, 1x/2x = register ring depth 1/2
-  if (cfg_t < 0) { const char *e = getenv("BNB_B200_GEMV_CFG"); cfg_t = e ? atoi(e) : 34; }
+  if (cfg_t < 0) { const char *e = getenv("BNB_B200_GEMV_CFG"); cfg_t = e ? atoi(e) : 0; }
   if (VEC4 && impl_bc && a.batch == 1 && cfg_t >= 30) {
     const int warps = (cfg_t % 10) * 4;
     const int tiles = ceil_div(a.N, 16);
@@ -1271,29 +1280,48 @@ static void launch_mma_inst(const GemvArgs &a) {
     }
   }
   if (VEC4 && impl_bc && a.batch == 1) {
-    // block-column kernel: shared memory = 64 KB alignment slack + LUT + head + x (144 B per block) + partial sums
-    static int cfg = -1;   // experiment knob: BNB_B200_GEMV_CFG = <depth><warps/4>, e.g. 24 = depth 2, 16 warps
-    if (cfg < 0) { const char *e = getenv("BNB_B200_GEMV_CFG"); cfg = e ? atoi(e) : 24; if (cfg >= 30) cfg = 24; }
-    const int warps = (cfg % 10) * 4;
+    // block-column kernel, register ring.  Default: 8-warp CTAs, two per SM (<= 113 KB of shared memory and <= 128
+    // registers each), so consecutive GEMVs of a stream overlap through programmatic dependent launch; 16-warp
+    // CTAs, one per SM, when x + partial sums do not fit twice (K > ~16K).
+    static int cfg = -1;   // experiment knob: BNB_B200_GEMV_CFG = <depth><warps/4>, e.g. 22 = depth 2, 8 warps
+    if (cfg < 0) { const char *e = getenv("BNB_B200_GEMV_CFG"); cfg = e ? atoi(e) : 0; if (cfg >= 30) cfg = 0; }
     const int tiles = ceil_div(a.N, 16);
-    const int grid = tiles < num_sms[dev] ? tiles : num_sms[dev];
     const int xblocks = ceil_div(a.K, 512) * 8;
-    const int ntl_max = ceil_div(tiles, grid);
-    const size_t need = 65536 + 65536 + kBcHead + (size_t)xblocks * kBcXPitch + (size_t)ntl_max * warps * 16 * sizeof(float);
+    auto smem_need = [&](int warps, int grid) {
+      return (size_t)65536 + kBcHead + (size_t)xblocks * kBcXPitch + (size_t)ceil_div(tiles, grid) * warps * 16 * sizeof(float);
+    };
+    int warps = cfg ? (cfg % 10) * 4 : 8;
+    int per_sm = warps <= 8 ? 2 : 1;
+    int grid = tiles < num_sms[dev] * per_sm ? tiles : num_sms[dev] * per_sm;
+    if (!cfg && smem_need(warps, grid) > (size_t)(113 * 1024)) {
+      warps = 16; per_sm = 1;
+      grid = tiles < num_sms[dev] ? tiles : num_sms[dev];
+    }
+    const size_t need = smem_need(warps, grid);
+    const int depth = cfg ? cfg / 10 : 2;
     if (need <= (size_t)kBcSmemMax) {
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3(grid); lc.blockDim = dim3(warps * 32); lc.dynamicSmemBytes = need; lc.stream = current_stream();
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      lc.attrs = attr; lc.numAttrs = pdl_off ? 0 : 1;
 #define BC_LAUNCH(EXP_, DEPTH_, WARPS_)                                                                                  \
   do {                                                                                                                  \
     auto kfn = k_gemv4_bc<T, NESTED, EXP_, DEPTH_, WARPS_>;                                                             \
     latch_error(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kBcSmemMax), "gemv bc smem attr"); \
-    kfn<<<grid, WARPS_ * 32, need, current_stream()>>>(a2, xblocks, tiles);                                             \
+    latch_error(cudaLaunchKernelEx(&lc, kfn, a2, xblocks, tiles), "gemv_4bit (block-column) launch");                  \
   } while (0)
-      if (exp_mode == 1) BC_LAUNCH(1, 2, 16);
-      else if (exp_mode == 2 && cfg == 15) BC_LAUNCH(2, 1, 20);
-      else if (exp_mode == 2 && cfg == 16) BC_LAUNCH(2, 1, 24);
+      if (exp_mode == 1 && warps == 8) BC_LAUNCH(1, 2, 8);
+      else if (exp_mode == 2 && warps == 8) BC_LAUNCH(2, 2, 8);
+      else if (exp_mode == 1) BC_LAUNCH(1, 2, 16);
       else if (exp_mode == 2) BC_LAUNCH(2, 2, 16);
-      else if (cfg == 14) BC_LAUNCH(0, 1, 16);
-      else if (cfg == 15) BC_LAUNCH(0, 1, 20);
-      else if (cfg == 16) BC_LAUNCH(0, 1, 24);
+      else if (warps == 8 && depth == 1) BC_LAUNCH(0, 1, 8);
+      else if (warps == 8) BC_LAUNCH(0, 2, 8);
+      else if (warps == 12 && depth == 1) BC_LAUNCH(0, 1, 12);
+      else if (warps == 16 && depth == 1) BC_LAUNCH(0, 1, 16);
+      else if (warps == 20) BC_LAUNCH(0, 1, 20);
+      else if (warps == 24) BC_LAUNCH(0, 1, 24);
       else BC_LAUNCH(0, 2, 16);
 #undef BC_LAUNCH
       check_launch("gemv_4bit (block-column)");
