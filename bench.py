@@ -204,6 +204,10 @@ def main():
     ap.add_argument("--workload", default="llama2-7b", choices=["llama2-7b", "llama3-70b"])
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
+                    help="N>1: output all-gather fused into the GEMV epilogue (peer stores), or one NCCL all-gather per linear")
+    ap.add_argument("--sync", default="kernel", choices=["kernel", "barrier"],
+                    help="N>1 fused collective: ordering folded into the GEMV kernels, or one symmetric-memory barrier launch per consumer group")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph of the step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -251,9 +255,54 @@ def main():
     outs = [torch.empty(B, st.shape[0], device=dev, dtype=dtype) for (_, st, _, _) in mats]
     gathered = [torch.empty(world, B, st.shape[0], device=dev, dtype=dtype) for (_, st, _, _) in mats] if world > 1 else None
     n_launch_per_step = len(mats)
+    # multi-GPU: the output all-gather is fused into the GEMV epilogue (peer stores over NVLink into symmetric
+    # memory); one signal-pad barrier per group of linears that feed the same consumer in a decoder layer
+    # (q/k/v | o | gate/up | down) stands for the point where that consumer would wait.  --collective nccl keeps
+    # the plain NCCL all-gather per linear.
+    peers = None
+    collective = "none"
+    if world > 1:
+        collective = "nccl-allgather-per-linear"
+        if args.collective == "fused" and B == 1:
+            try:
+                from bnb_b200.parallel import PeerOutputBuffers, sharded_gemv_push
+                peers = PeerOutputBuffers([N for (_, _, N, _) in mats], dtype, dev)
+                collective = "fused-epilogue-p2p-stores+symm-barrier-per-consumer-group"
+                if args.sync == "kernel":
+                    peers.enable_kernel_sync(ngroups=args.layers * 4 if len(shapes) == 7 else len(mats))
+                    collective = "fused-epilogue-p2p-stores+in-kernel-signal/wait-per-consumer-group"
+            except Exception as e:  # noqa: BLE001
+                sys.stderr.write(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL all-gather\n")
+                peers = None
+    per_layer = len(shapes)
+    group_ends = {2, 3, 5, 6} if per_layer == 7 else set(range(per_layer))
+
+    group_starts = {0, 3, 4, 6} if per_layer == 7 else set(range(per_layer))
+    kernel_sync = peers is not None and args.sync == "kernel"
+    syncs = None
+    if kernel_sync:   # one descriptor per linear: group index, "ends a group" -> signal, "starts a group" -> wait
+        syncs, gi = [], 0
+        for i in range(len(mats)):
+            pos = i % per_layer
+            syncs.append(peers.sync_desc(gi, pos in group_ends, pos in group_starts))
+            if pos in group_ends:
+                gi += 1
+
+    def fused_linear(i, x, q, st):
+        if kernel_sync:
+            sharded_gemv_push(x, q, st, peers, i, syncs[i])
+            if i == len(mats) - 1:
+                peers.bump_epoch()      # next pass counts on: sequence numbers never repeat across graph replays
+        else:
+            sharded_gemv_push(x, q, st, peers, i)
+            if (i % per_layer) in group_ends:
+                peers.barrier()
 
     def step_eager():
         for i, (q, st, N, K) in enumerate(mats):
+            if peers is not None:
+                fused_linear(i, xs[i], q, st)
+                continue
             if B == 1:
                 F.gemv_4bit(xs[i], q.t(), out=outs[i], state=st)
             else:
@@ -293,19 +342,33 @@ def main():
     x_dev = torch.empty(B, k_total, device=dev, dtype=dtype)
     y_dev = torch.empty(B, n_total, device=dev, dtype=dtype)
     y_host = torch.empty(B, n_total, dtype=dtype).pin_memory()
+    offs_n = [0]
+    for (_, _, N, _) in mats:
+        offs_n.append(offs_n[-1] + N)
 
     def e2e_body():
         # public API end to end: pinned host activations -> device, Linear4bit's matmul_4bit per matrix, outputs -> host
         x_dev.copy_(x_host, non_blocking=True)
         ko = no = 0
         for i, (q, st, N, K) in enumerate(mats):
-            y = bnb_b200.matmul_4bit(x_dev[:, ko:ko + K], q.t(), quant_state=st)
-            if world > 1:
-                y = all_gather_features(y, world)
-            y_dev[:, no:no + N] = y.reshape(B, N)
+            if peers is not None:
+                fused_linear(i, x_dev[:, ko:ko + K], q, st)
+            else:
+                y = bnb_b200.matmul_4bit(x_dev[:, ko:ko + K], q.t(), quant_state=st)
+                if world > 1:
+                    y = all_gather_features(y, world)
+                y_dev[:, no:no + N] = y.reshape(B, N)
             ko += K
             no += N
-        y_host.copy_(y_dev, non_blocking=True)
+        if kernel_sync:
+            peers.barrier()      # the host read below consumes every gathered vector of the pass
+        if peers is not None and peers.offsets[-1] + peers.sizes[-1] == n_total:
+            y_host.copy_(peers.buf[:n_total].view(B, n_total), non_blocking=True)   # gathered vectors, straight from symmetric memory
+        else:
+            if peers is not None:
+                for j, (_, _, Nj, _) in enumerate(mats):
+                    y_dev[:, offs_n[j]:offs_n[j] + Nj] = peers.full(j)
+            y_host.copy_(y_dev, non_blocking=True)
 
     e2e_launch, e2e_graphed = capture(e2e_body)
 
@@ -381,7 +444,7 @@ def main():
                        "blocksize": 64, "nested_absmax": True, "algorithmic_bytes_per_step": alg_bytes,
                        "l2": f"inputs larger than L2 ({alg_bytes / 1e6:.0f} MB of weights per step, distinct per launch)",
                        "launch": "cuda-graph" if graphed else "eager",
-                       "parallelism": f"n-shard{world}+allgather" if world > 1 else "single"},
+                       "parallelism": f"n-shard{world}" if world > 1 else "single", "collective": collective},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "k_gemv4_bc<bf16,nested>", "peak_source": peak_kind,
                          "bytes_per_launch": bytes_per_launch, "launch_us": launch_ms * 1e3},
@@ -397,9 +460,18 @@ def main():
         elif not args.no_cpu_baseline:
             line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": None, "kind": "reference",
                                     "sample": "reported at N=1 only"}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL / symmetric-memory teardown after graph capture has hung at exit on this stack: every number is
+        # out, so synchronise, flush and leave without running the destructors
+        try:
+            dist.barrier()
+            torch.cuda.synchronize()
+        except Exception:  # noqa: BLE001
+            pass
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

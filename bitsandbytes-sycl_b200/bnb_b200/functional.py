@@ -443,11 +443,21 @@ def dequantize_4bit(A: Tensor, quant_state: Optional[QuantState] = None, absmax:
 # ------------------------------------------------------------------------------------------------
 # 4-bit GEMV / GEMM (reference :1961-2060; batch > 1: autograd/_functions.py:490-518)
 # ------------------------------------------------------------------------------------------------
-def gemv_4bit(A: Tensor, B: Tensor, out: Optional[Tensor] = None, transposed_A=False, transposed_B=False, state=None):
+class GemvSync(ct.Structure):
+    """bnb_gemv_sync_t of include/bnb_b200.h: cross-GPU signal / wait folded into the GEMV kernels."""
+    _fields_ = [("sig_local", ct.c_void_p), ("sig_peer", ct.c_void_p * 7), ("epoch", ct.c_void_p),
+                ("cta_counter", ct.c_void_p), ("gidx", ct.c_int), ("ngroups", ct.c_int), ("do_signal", ct.c_int),
+                ("do_wait", ct.c_int)]
+
+
+def gemv_4bit(A: Tensor, B: Tensor, out: Optional[Tensor] = None, transposed_A=False, transposed_B=False, state=None,
+              peer_outs=None, sync: Optional[GemvSync] = None):
     """out[.., N] = A[.., K] @ dequant(B)[N, K]^T for a single activation row.
     Reference: de-nest absmax (2 launches) then cgemm_4bit_inference_naive_<T>.  Here, when the state is
     nested and the fused path is on, ONE launch (cgemm_4bit_inference_nested_<T>) reads the uint8 absmax
-    directly; the de-nest arithmetic inside the kernel is the same fl(fl(code2[q]*absmax2)+offset)."""
+    directly; the de-nest arithmetic inside the kernel is the same fl(fl(code2[q]*absmax2)+offset).
+    ADDITIVE `peer_outs`: list of peer-mapped device addresses (ints) -- the kernel stores the result there too
+    (N-sharded linear on one NVLink box: the output all-gather fused into the epilogue, parallel.py)."""
     if state is None:
         raise ValueError("state cannot None. gem_4bit( ) requires the state from quantize_4bit( )")
     if A.numel() != A.shape[-1]:
@@ -478,12 +488,25 @@ def gemv_4bit(A: Tensor, B: Tensor, out: Optional[Tensor] = None, transposed_A=F
             offset = state._offset_host = float(state.offset)
         prev = pre_call(A.device)
         is_on_gpu([B, A, out, state.absmax, s2.absmax, s2.code, code])
+        if peer_outs:
+            arr = (ct.c_void_p * len(peer_outs))(*[ct.c_void_p(int(p)) for p in peer_outs])
+            getattr(lib, f"cgemm_4bit_inference_nested_push_{_SUFFIX[A.dtype]}")(
+                ct.c_int32(m), ct.c_int32(n), ct.c_int32(k), get_ptr(A), get_ptr(B), get_ptr(state.absmax),
+                get_ptr(s2.absmax), get_ptr(s2.code), ct.c_float(offset), get_ptr(code), get_ptr(out),
+                ct.c_int32(lda), ct.c_int32(ldb), ct.c_int32(ldc), ct.c_int32(state.blocksize), ct.c_int32(s2.blocksize),
+                arr, ct.c_int32(len(peer_outs)), ct.byref(sync) if sync is not None else None)
+            post_call(prev)
+            if lib.cbnb_last_error():
+                raise RuntimeError(lib.cbnb_last_error_string().decode())
+            return out
         getattr(lib, f"cgemm_4bit_inference_nested_{_SUFFIX[A.dtype]}")(
             ct.c_int32(m), ct.c_int32(n), ct.c_int32(k), get_ptr(A), get_ptr(B), get_ptr(state.absmax),
             get_ptr(s2.absmax), get_ptr(s2.code), ct.c_float(offset), get_ptr(code), get_ptr(out),
             ct.c_int32(lda), ct.c_int32(ldb), ct.c_int32(ldc), ct.c_int32(state.blocksize), ct.c_int32(s2.blocksize))
         post_call(prev)
         return out
+    if peer_outs:
+        raise NotImplementedError("peer_outs needs the fused nested GEMV (nested absmax, fp16/bf16, blocksize 64)")
     absmax = state.absmax
     if state.nested:
         absmax = dequantize_blockwise(state.absmax, state.state2)
@@ -505,6 +528,8 @@ def gemm_4bit(A: Tensor, B: Tensor, state: QuantState, bias: Optional[Tensor] = 
     (dequantize_4bit + F.linear, autograd/_functions.py:507)."""
     if not FUSED_GEMM_4BIT or A.dtype not in (torch.float16, torch.bfloat16):
         return None
+    if state.dtype not in (A.dtype, torch.float32):
+        return None     # reference: dequantize to state.dtype, then .to(A.dtype) -- two roundings the fused kernel does not do
     N, K = state.shape
     A2 = A.reshape(-1, A.shape[-1]).contiguous()
     batch = A2.shape[0]

@@ -84,3 +84,92 @@ def all_gather_features(y_local: torch.Tensor, world: int, group=None, out: Opti
     gathered = torch.empty((world, batch, per), dtype=y2.dtype, device=y2.device) if out is None else out
     dist.all_gather_into_tensor(gathered.view(world * batch, per), y2, group=group)
     return gathered.permute(1, 0, 2).reshape(*y_local.shape[:-1], world * per)
+
+
+class PeerOutputBuffers:
+    """Symmetric-memory output vectors of an N-sharded GEMV stack (batch 1) on the GPUs of one NVLink box.
+
+    Every rank holds the FULL [1, N_i] output of each linear i in one symmetric allocation
+    (torch.distributed._symmetric_memory: cuMem + peer mappings over NVLink).  Rank r's GEMV writes its slice
+    [r*N_i/g, (r+1)*N_i/g) into its own copy AND -- through the peer-mapped addresses handed to the kernel -- into
+    every peer's copy: the output all-gather of SURVEY 8e happens in the GEMV epilogue, no NCCL launch.
+    `barrier()` (symmetric-memory signal-pad barrier, one small kernel) is what a consumer of the gathered
+    vectors waits on."""
+
+    def __init__(self, sizes: List[int], dtype: torch.dtype, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.sizes = list(sizes)
+        self.offsets = []
+        off = 0
+        for n in self.sizes:
+            assert n % self.world == 0
+            self.offsets.append(off)
+            off += (n + 63) // 64 * 64           # keep every vector 128-byte aligned
+        self.buf = symm_mem.empty(max(off, 64), dtype=dtype, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.itemsize = self.buf.element_size()
+        self.base_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+
+    def full(self, i: int) -> torch.Tensor:
+        return self.buf[self.offsets[i]:self.offsets[i] + self.sizes[i]].view(1, -1)
+
+    def local_slice(self, i: int) -> torch.Tensor:
+        per = self.sizes[i] // self.world
+        o = self.offsets[i] + self.rank * per
+        return self.buf[o:o + per].view(1, per)
+
+    def peer_ptrs(self, i: int) -> List[int]:
+        per = self.sizes[i] // self.world
+        o = (self.offsets[i] + self.rank * per) * self.itemsize
+        return [self.base_ptrs[p] + o for p in range(self.world) if p != self.rank]
+
+    def barrier(self, channel: int = 0) -> None:
+        self.hdl.barrier(channel=channel)
+
+    # ---- in-kernel ordering (no barrier launch): signal slots in symmetric memory + a per-pass epoch
+    def enable_kernel_sync(self, ngroups: int) -> None:
+        import ctypes as ct
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.ngroups = ngroups
+        self.sig = symm_mem.empty(64, dtype=torch.int32, device=self.buf.device)
+        self.sig.zero_()
+        self.sig_hdl = symm_mem.rendezvous(self.sig, self.group)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=self.buf.device)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=self.buf.device)
+        torch.cuda.synchronize()
+        self.sig_hdl.barrier(channel=0)
+        sig_ptrs = [int(p) for p in self.sig_hdl.buffer_ptrs]
+        others = [p for p in range(self.world) if p != self.rank]
+        self._sig_peer = []
+        for p in others:   # my compact slot inside peer p's array: my index among p's peers
+            mine = self.rank if self.rank < p else self.rank - 1
+            self._sig_peer.append(sig_ptrs[p] + 4 * mine)
+        self._ct = ct
+
+    def sync_desc(self, gidx: int, do_signal: bool, do_wait: bool) -> "F.GemvSync":
+        s = F.GemvSync()
+        s.sig_local = self.sig.data_ptr()
+        for k, a in enumerate(self._sig_peer):
+            s.sig_peer[k] = a
+        s.epoch = self.epoch.data_ptr()
+        s.cta_counter = self.counter.data_ptr()
+        s.gidx, s.ngroups, s.do_signal, s.do_wait = gidx, self.ngroups, int(do_signal), int(do_wait)
+        return s
+
+    def bump_epoch(self) -> None:
+        """once per pass over the stack (stream-ordered, graph-capturable)"""
+        import ctypes as ct
+        F.lib.cbnb_set_stream(ct.c_void_p(torch.cuda.current_stream().cuda_stream))
+        F.lib.cbnb_epoch_bump(ct.c_void_p(self.epoch.data_ptr()))
+
+
+def sharded_gemv_push(x: torch.Tensor, packed_shard: torch.Tensor, state_shard: QuantState, peers: PeerOutputBuffers,
+                      i: int, sync=None) -> torch.Tensor:
+    """Rank-local GEMV of linear i whose epilogue stores the output slice into every rank's full vector."""
+    return F.gemv_4bit(x, packed_shard.t(), out=peers.local_slice(i), state=state_shard, peer_outs=peers.peer_ptrs(i),
+                       sync=sync)

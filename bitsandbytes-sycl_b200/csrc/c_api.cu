@@ -29,7 +29,9 @@ template <typename T, int QT> void dequantize_blockwise(const float *, const uns
 long long selftest_quant_lut(int qtype);
 void gemv_probe(unsigned long long *out2);
 template <typename T> void gemv_4bit(int, int, int, const T *, const unsigned char *, const float *, const float *, T *, int, int, int, int);
-template <typename T> void gemv_4bit_nested(int, int, int, const T *, const unsigned char *, const unsigned char *, const float *, const float *, float, const float *, T *, int, int, int, int, int);
+struct GemvSync;
+void epoch_bump(unsigned int *epoch);
+template <typename T> void gemv_4bit_nested(int, int, int, const T *, const unsigned char *, const unsigned char *, const float *, const float *, float, const float *, T *, int, int, int, int, int, void *const *, int, const GemvSync *);
 template <typename T> int gemm_4bit(int, int, int, const T *, const unsigned char *, const float *, const float *, const T *, T *, int);
 void get_col_row_stats(const __half *, float *, float *, int *, float, int, int);
 void double_rowcol_quant(const __half *, const float *, const float *, signed char *, signed char *, int *, int *, __half *, const int *, float, int, int);
@@ -94,9 +96,15 @@ void cgemm_4bit_inference_naive_bf16(int m, int n, int k, void *A, unsigned char
 void cgemm_4bit_inference_naive_fp32(int m, int n, int k, float *A, unsigned char *B, float *absmax, float *datatype, float *out, int lda, int ldb, int ldc, int blocksize) {
   gemv_4bit<float>(m, n, k, A, B, absmax, datatype, out, lda, ldb, ldc, blocksize); }
 void cgemm_4bit_inference_nested_fp16(int m, int n, int k, void *A, unsigned char *B, unsigned char *qabsmax, float *absmax2, float *code2, float offset, float *datatype, void *out, int lda, int ldb, int ldc, int blocksize, int blocksize2) {
-  gemv_4bit_nested<half_t>(m, n, k, (half_t *)A, B, qabsmax, absmax2, code2, offset, datatype, (half_t *)out, lda, ldb, ldc, blocksize, blocksize2); }
+  gemv_4bit_nested<half_t>(m, n, k, (half_t *)A, B, qabsmax, absmax2, code2, offset, datatype, (half_t *)out, lda, ldb, ldc, blocksize, blocksize2, nullptr, 0, nullptr); }
 void cgemm_4bit_inference_nested_bf16(int m, int n, int k, void *A, unsigned char *B, unsigned char *qabsmax, float *absmax2, float *code2, float offset, float *datatype, void *out, int lda, int ldb, int ldc, int blocksize, int blocksize2) {
-  gemv_4bit_nested<bf16_t>(m, n, k, (bf16_t *)A, B, qabsmax, absmax2, code2, offset, datatype, (bf16_t *)out, lda, ldb, ldc, blocksize, blocksize2); }
+  gemv_4bit_nested<bf16_t>(m, n, k, (bf16_t *)A, B, qabsmax, absmax2, code2, offset, datatype, (bf16_t *)out, lda, ldb, ldc, blocksize, blocksize2, nullptr, 0, nullptr); }
+
+void cgemm_4bit_inference_nested_push_fp16(int m, int n, int k, void *A, unsigned char *B, unsigned char *qabsmax, float *absmax2, float *code2, float offset, float *datatype, void *out, int lda, int ldb, int ldc, int blocksize, int blocksize2, void **peer_outs, int npeers, const bnb_gemv_sync_t *sync) {
+  gemv_4bit_nested<half_t>(m, n, k, (half_t *)A, B, qabsmax, absmax2, code2, offset, datatype, (half_t *)out, lda, ldb, ldc, blocksize, blocksize2, peer_outs, npeers, reinterpret_cast<const GemvSync *>(sync)); }
+void cgemm_4bit_inference_nested_push_bf16(int m, int n, int k, void *A, unsigned char *B, unsigned char *qabsmax, float *absmax2, float *code2, float offset, float *datatype, void *out, int lda, int ldb, int ldc, int blocksize, int blocksize2, void **peer_outs, int npeers, const bnb_gemv_sync_t *sync) {
+  gemv_4bit_nested<bf16_t>(m, n, k, (bf16_t *)A, B, qabsmax, absmax2, code2, offset, datatype, (bf16_t *)out, lda, ldb, ldc, blocksize, blocksize2, peer_outs, npeers, reinterpret_cast<const GemvSync *>(sync)); }
+void cbnb_epoch_bump(unsigned int *epoch) { epoch_bump(epoch); }
 
 // ---------------------------------------------------------------- fused 4-bit GEMM (additive)
 int cgemm_4bit_fp16(int batch, int N, int K, void *A, unsigned char *B, float *absmax, float *datatype, void *bias, void *out, int blocksize) {

@@ -67,6 +67,29 @@ struct GemvArgs {
   float offset;
   const float *code;         // fp32[16]
   void *out;                 // [batch, N] T
+  // multi-GPU (N-sharded linear): the same output slice is also stored into the peers' copies of the full
+  // output vector through NVLink peer mappings -- the all-gather happens in the GEMV epilogue
+  void *peer_out[7];
+  int npeers;
+  // cross-GPU ordering of the gathered vectors, folded into the kernels (no barrier launch): the kernel that ends
+  // a consumer group publishes sequence number seq+1 into every peer's signal slot once ALL its CTAs have stored
+  // (and fenced) their slices; the kernel that starts a group waits -- after griddepcontrol.wait, before it reads
+  // x -- until every peer has published >= its own seq.  seq = *epoch * ngroups + gidx; epoch is bumped once per
+  // step by k_epoch_bump so that replayed CUDA graphs keep counting.
+  unsigned int *sig_local;      // [world] slots on this GPU, slot p written by peer p (nullptr: no sync)
+  unsigned int *sig_peer[7];    // peers' slot for this rank
+  const unsigned int *epoch;
+  unsigned int *cta_counter;    // per-GPU scratch, zero at rest
+  int gidx, ngroups, do_signal, do_wait;
+};
+
+// host-side mirror of bnb_gemv_sync_t (include/bnb_b200.h)
+struct GemvSync {
+  unsigned int *sig_local;
+  unsigned int *sig_peer[7];
+  const unsigned int *epoch;
+  unsigned int *cta_counter;
+  int gidx, ngroups, do_signal, do_wait;
 };
 
 struct ChunkRegs {
@@ -728,6 +751,20 @@ __device__ __forceinline__ void lds_x4_pred(uint32_t (&b)[4], uint32_t saddr, ui
                : "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]) : "r"(saddr), "r"(active));
 }
 
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__global__ void k_epoch_bump(unsigned int *epoch) { *epoch += 1; }
+void epoch_bump(unsigned int *epoch) {
+  k_epoch_bump<<<1, 1, 0, current_stream()>>>(epoch);
+  check_launch("epoch_bump");
+}
+
 // debug probe (flags bit 1): SM cycles and nanoseconds spent by CTA 0 -> effective SM clock under this kernel's load
 __device__ unsigned long long g_gemv_probe[2];
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -827,6 +864,19 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
     }
     for (int i = tid; i < ntl * WARPS * 16; i += CT) s_part[i] = 0.f;
     asm volatile("griddepcontrol.wait;" ::: "memory");     // x (and out) belong to the previous kernel until here
+    if (a.sig_local != nullptr && a.do_wait) {
+      // first kernel of a consumer group on an N-sharded stack: the gathered vectors of the previous group must
+      // be complete on this GPU, i.e. every peer has published a sequence number >= ours (bounded spin: trap, never hang)
+      if (tid < a.npeers) {
+        const unsigned int target = ld_acquire_sys(a.epoch) * (unsigned int)a.ngroups + (unsigned int)a.gidx;
+        const unsigned int *slot = a.sig_local + tid;
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(slot) - target) < 0) {
+          if (clock64() - t0 > 4000000000ll) __trap();
+        }
+      }
+      __syncthreads();
+    }
     const uint4 *xg = reinterpret_cast<const uint4 *>(a.x);
     const int pieces = x_blocks_padded * 8, valid = a.K >> 3;
     for (int p0 = tid; p0 < pieces; p0 += 4 * CT) {   // four independent loads in flight per thread
@@ -921,7 +971,24 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
 #pragma unroll
     for (int wq = 0; wq < WARPS; wq++) sum += p[wq * 16];
     const int r = (t_begin + tile_l) * 16 + row;
-    if (r < a.N) reinterpret_cast<T *>(a.out)[r] = from_float<T>(sum);
+    if (r < a.N) {
+      const T v = from_float<T>(sum);
+      reinterpret_cast<T *>(a.out)[r] = v;
+      for (int pr = 0; pr < a.npeers; pr++) reinterpret_cast<T *>(a.peer_out[pr])[r] = v;   // NVLink P2P stores
+    }
+  }
+  if (a.sig_local != nullptr && a.do_signal) {
+    __threadfence_system();                       // this thread's peer stores are visible system-wide
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int done = atomicAdd(a.cta_counter, 1u);
+      if (done == gridDim.x - 1) {                // last CTA of the grid: the whole slice is out
+        *a.cta_counter = 0u;
+        __threadfence_system();
+        const unsigned int seq = ld_acquire_sys(a.epoch) * (unsigned int)a.ngroups + (unsigned int)a.gidx + 1u;
+        for (int pr = 0; pr < a.npeers; pr++) st_release_sys(a.sig_peer[pr], seq);
+      }
+    }
   }
   if ((a.flags & 2) && blockIdx.x == 0 && tid == 0) {
     g_gemv_probe[0] = clock64() - probe_c;
@@ -1246,7 +1313,7 @@ static void launch_mma_inst(const GemvArgs &a) {
   if (pdl_off < 0) { const char *e = getenv("BNB_B200_GEMV_PDL"); pdl_off = (e && e[0] == '0') ? 1 : 0; }
   static int cfg_t = -1;   // experiment knob: BNB_B200_GEMV_CFG = <impl><warps/4>: 3x = TMA ring, 1x/2x = register ring depth 1/2
   if (cfg_t < 0) { const char *e = getenv("BNB_B200_GEMV_CFG"); cfg_t = e ? atoi(e) : 0; }
-  if (VEC4 && impl_bc && a.batch == 1 && cfg_t >= 30) {
+  if (VEC4 && impl_bc && a.batch == 1 && cfg_t >= 30 && a.npeers == 0) {
     const int warps = (cfg_t % 10) * 4;
     const int tiles = ceil_div(a.N, 16);
     const int grid = tiles < num_sms[dev] ? tiles : num_sms[dev];
@@ -1328,6 +1395,7 @@ static void launch_mma_inst(const GemvArgs &a) {
       return;
     }
   }
+  if (a.npeers > 0) { latch_error(cudaErrorInvalidValue, "gemv_4bit: peer outputs are only available in the block-column kernel"); return; }
   if (VEC4 && !impl_reg && exp_mode == 0) {
     static bool attr2[64] = {false};
     if (!attr2[dev]) {
@@ -1381,7 +1449,8 @@ void gemv_4bit(int m, int n, int k, const T *A, const unsigned char *B, const fl
 template <typename T>
 void gemv_4bit_nested(int m, int n, int k, const T *A, const unsigned char *B, const unsigned char *qabsmax,
                       const float *absmax2, const float *code2, float offset, const float *datatype, T *out,
-                      int lda, int ldb, int ldc, int blocksize, int blocksize2) {
+                      int lda, int ldb, int ldc, int blocksize, int blocksize2, void *const *peer_outs, int npeers,
+                      const GemvSync *sync) {
   (void)lda; (void)ldc;
   if (m <= 0 || k <= 0) return;
   if (n < 1 || n > 8 || blocksize2 <= 0 || (blocksize2 & (blocksize2 - 1)) != 0 || !fast_path_ok(k, ldb, blocksize, A, B)) {
@@ -1392,13 +1461,27 @@ void gemv_4bit_nested(int m, int n, int k, const T *A, const unsigned char *B, c
   a.N = m; a.K = k; a.batch = n; a.blocksize = blocksize;
   a.x = A; a.B = B; a.qabsmax = qabsmax; a.absmax2 = absmax2; a.code2 = code2; a.offset = offset;
   a.code = datatype; a.out = out;
+  if (npeers > 0) {
+    // peer stores exist only in the block-column kernel (batch 1, blocksize 64, K % 256 == 0, K small enough for shared memory)
+    if (npeers > 7 || n != 1 || blocksize != 64 || (k % 256) != 0 || k > 28672 || !peer_outs) {
+      latch_error(cudaErrorInvalidValue, "gemv_4bit_nested: peer outputs need batch 1, blocksize 64, K % 256 == 0, <= 7 peers");
+      return;
+    }
+    a.npeers = npeers;
+    for (int i = 0; i < npeers; i++) a.peer_out[i] = peer_outs[i];
+    if (sync && sync->sig_local) {
+      a.sig_local = sync->sig_local; a.epoch = sync->epoch; a.cta_counter = sync->cta_counter;
+      a.gidx = sync->gidx; a.ngroups = sync->ngroups; a.do_signal = sync->do_signal; a.do_wait = sync->do_wait;
+      for (int i = 0; i < npeers; i++) a.sig_peer[i] = sync->sig_peer[i];
+    }
+  }
   launch_mma<T, true>(a, blocksize2);
 }
 
 template void gemv_4bit<float>(int, int, int, const float *, const unsigned char *, const float *, const float *, float *, int, int, int, int);
 template void gemv_4bit<__half>(int, int, int, const __half *, const unsigned char *, const float *, const float *, __half *, int, int, int, int);
 template void gemv_4bit<__nv_bfloat16>(int, int, int, const __nv_bfloat16 *, const unsigned char *, const float *, const float *, __nv_bfloat16 *, int, int, int, int);
-template void gemv_4bit_nested<__half>(int, int, int, const __half *, const unsigned char *, const unsigned char *, const float *, const float *, float, const float *, __half *, int, int, int, int, int);
-template void gemv_4bit_nested<__nv_bfloat16>(int, int, int, const __nv_bfloat16 *, const unsigned char *, const unsigned char *, const float *, const float *, float, const float *, __nv_bfloat16 *, int, int, int, int, int);
+template void gemv_4bit_nested<__half>(int, int, int, const __half *, const unsigned char *, const unsigned char *, const float *, const float *, float, const float *, __half *, int, int, int, int, int, void *const *, int, const GemvSync *);
+template void gemv_4bit_nested<__nv_bfloat16>(int, int, int, const __nv_bfloat16 *, const unsigned char *, const unsigned char *, const float *, const float *, float, const float *, __nv_bfloat16 *, int, int, int, int, int, void *const *, int, const GemvSync *);
 
 }  // namespace bnb

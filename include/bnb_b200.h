@@ -126,6 +126,26 @@ BNB_B200_API void cbnb_debug_gemv_probe(unsigned long long *cycles_ns);
 BNB_B200_API void cgemm_4bit_inference_nested_fp16(int m, int n, int k, void *A, unsigned char *B, unsigned char *qabsmax, float *absmax2, float *code2, float offset, float *datatype, void *out, int lda, int ldb, int ldc, int blocksize, int blocksize2);
 BNB_B200_API void cgemm_4bit_inference_nested_bf16(int m, int n, int k, void *A, unsigned char *B, unsigned char *qabsmax, float *absmax2, float *code2, float offset, float *datatype, void *out, int lda, int ldb, int ldc, int blocksize, int blocksize2);
 
+/* same GEMV for an N-sharded (column-parallel) linear on several GPUs of one NVLink box: `out` is this rank's
+ * slice inside its own copy of the full output vector; the kernel also stores the slice at the same offset into
+ * the peers' copies (peer_outs: HOST array of npeers <= 7 peer-mapped DEVICE pointers) -- the output all-gather of
+ * SURVEY 8e fused into the GEMV epilogue.  Needs n == 1, blocksize 64, K % 256 == 0.
+ * `sync` (may be NULL) folds the cross-GPU ordering into the kernels, no barrier launch: with do_signal the kernel
+ * publishes sequence number (*epoch * ngroups + gidx + 1) into every peer's slot (sig_peer[i] = address of THIS
+ * rank's slot inside peer i's signal array) once all its CTAs have stored and fenced; with do_wait it waits, before
+ * reading A, until every slot of sig_local (one per peer) holds >= (*epoch * ngroups + gidx).  cbnb_epoch_bump()
+ * increments *epoch on the launch stream (once per pass over the stack, so replayed CUDA graphs keep counting). */
+typedef struct {
+  unsigned int *sig_local;      /* [npeers] slots on this GPU, slot i written by peer i */
+  unsigned int *sig_peer[7];
+  const unsigned int *epoch;
+  unsigned int *cta_counter;    /* per-GPU scratch word, zero at rest */
+  int gidx, ngroups, do_signal, do_wait;
+} bnb_gemv_sync_t;
+BNB_B200_API void cgemm_4bit_inference_nested_push_fp16(int m, int n, int k, void *A, unsigned char *B, unsigned char *qabsmax, float *absmax2, float *code2, float offset, float *datatype, void *out, int lda, int ldb, int ldc, int blocksize, int blocksize2, void **peer_outs, int npeers, const bnb_gemv_sync_t *sync);
+BNB_B200_API void cgemm_4bit_inference_nested_push_bf16(int m, int n, int k, void *A, unsigned char *B, unsigned char *qabsmax, float *absmax2, float *code2, float offset, float *datatype, void *out, int lda, int ldb, int ldc, int blocksize, int blocksize2, void **peer_outs, int npeers, const bnb_gemv_sync_t *sync);
+BNB_B200_API void cbnb_epoch_bump(unsigned int *epoch);
+
 /* batch > 1 fused 4-bit GEMM (replaces dequantize_4bit + F.linear, autograd/_functions.py:490-518):
  * out[b, j] = sum_k A[b,k] * T(code[q(j,k)] * absmax[(j*K+k)/blocksize]) (+ bias[j]); A: [batch, K] T row-major,
  * B packed [N, K/2], out [batch, N] T. tcgen05 kind::f16, TMEM fp32 accumulators. */

@@ -1,0 +1,88 @@
+"""GPU parity: fused batch>1 4-bit GEMM (K4, tcgen05) through the C-ABI.
+The kernel dequantises with the reference's arithmetic -- w = T(fp32 code * fp32 absmax), one rounding
+(kernel_quant.cpp:1449-1450) -- so the oracle is: dequantised weight from the CPU restatement (bit-exact with the
+K2 kernel), product in fp64.  Tolerance (stated): fp32 accumulation + ONE output rounding,
+|y - y64| <= 2^-8 |y64| + 2^-9 rms(y64) for bf16, 2^-11 / 2^-12 for fp16."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import DT, from_bits, to_bits
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def F():
+    assert torch.cuda.is_available()
+    from bnb_b200 import functional
+    return functional
+
+
+def reference64(F, x, q, st, dtype, bias=None):
+    """fp64 product with the dequantised weight rounded to T exactly like dequantize_4bit."""
+    Wd = F.dequantize_4bit(q, st).to(DT[dtype])            # K2 kernel: bit-exact with the oracle (test_gpu_blockwise)
+    y = x.double().cpu().numpy() @ Wd.double().cpu().numpy().T
+    if bias is not None:
+        y = y + bias.double().cpu().numpy()[None, :]
+    return y
+
+
+CASES = [
+    (16, 256, 512, "bf16", True, 64, False),
+    (5, 130, 1024, "bf16", False, 64, True),       # batch not a multiple of 16, N not a multiple of 128, bias
+    (33, 384, 4096, "fp16", True, 64, True),
+    (256, 384, 2048, "bf16", True, 64, False),     # widest activation tile
+    (32, 128, 8192, "bf16", True, 64, True),       # one row tile -> split-K + finalize
+    (64, 4096, 14336, "bf16", True, 64, False),    # Llama-3-8B down projection: split-K
+    (16, 1024, 4096, "fp16", False, 128, False),   # blocksize 128
+]
+
+
+@pytest.mark.parametrize("batch,N,K,dtype,nested,blocksize,with_bias", CASES)
+def test_gemm_4bit_vs_fp64(F, batch, N, K, dtype, nested, blocksize, with_bias):
+    torch.manual_seed(batch * 7 + N)
+    W = (torch.randn(N, K) * 0.02).to(DT[dtype])
+    x = torch.randn(batch, K).to(DT[dtype])
+    bias = (torch.randn(N) * 0.1).to(DT[dtype]).cuda() if with_bias else None
+    q, st = F.quantize_4bit(W.cuda(), blocksize=blocksize, compress_statistics=nested, quant_type="nf4")
+    y = F.gemm_4bit(x.cuda(), q, st, bias=bias)
+    assert y is not None, "fused kernel refused a supported shape"
+    assert y.shape == (batch, N) and y.dtype == DT[dtype]
+    y64 = reference64(F, x, q, st, dtype, bias)
+    yk = y.double().cpu().numpy()
+    rel, noise = {"bf16": (2.0 ** -8, 2.0 ** -9), "fp16": (2.0 ** -11, 2.0 ** -12)}[dtype]
+    rms = np.sqrt(np.mean(y64 ** 2))
+    assert np.all(np.isfinite(yk))
+    assert np.all(np.abs(yk - y64) <= rel * np.abs(y64) + noise * rms)
+    # and against the reference's own composition (dequantize_4bit + F.linear): same weights, library GEMM
+    y_ref = torch.nn.functional.linear(x.cuda(), F.dequantize_4bit(q, st).to(DT[dtype]), bias)
+    assert np.all(np.abs(yk - y_ref.double().cpu().numpy()) <= 2 * rel * np.abs(y64) + 2 * noise * rms)
+
+
+def test_gemm_4bit_deterministic_and_module_path(F):
+    from bnb_b200.nn import LinearNF4
+    torch.manual_seed(3)
+    lin = LinearNF4(2048, 768, bias=True, compute_dtype=torch.bfloat16).cuda()
+    x = torch.randn(4, 24, 2048, dtype=torch.bfloat16, device="cuda")
+    with torch.no_grad():
+        y1 = lin(x)
+        y2 = lin(x)
+    assert y1.shape == (4, 24, 768)
+    assert torch.equal(y1.view(torch.int16), y2.view(torch.int16))
+    Wd = F.dequantize_4bit(lin.weight.data, lin.weight.quant_state).to(torch.bfloat16)
+    y_ref = torch.nn.functional.linear(x, Wd, lin.bias.to(torch.bfloat16))
+    assert (y1.float() - y_ref.float()).abs().max().item() <= 2.0 ** -7 * y_ref.float().abs().max().item()
+
+
+def test_gemm_4bit_refuses_what_it_cannot_do(F):
+    """K not a multiple of 64 -> rc 1 -> Python falls back to the reference composition (still on the GPU)."""
+    torch.manual_seed(0)
+    W = (torch.randn(64, 96) * 0.02).bfloat16()
+    q, st = F.quantize_4bit(W.cuda(), blocksize=64, quant_type="nf4")      # numel 6144 = 96 blocks
+    x = torch.randn(8, 96).bfloat16().cuda()
+    assert F.gemm_4bit(x, q, st) is None
+    import bnb_b200
+    y = bnb_b200.matmul_4bit(x, q.t(), quant_state=st)
+    assert y.shape == (8, 64) and torch.isfinite(y).all()

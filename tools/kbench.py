@@ -125,6 +125,31 @@ def bench_gemv(iters, shapes=None, dtypes=(torch.bfloat16,)):
             torch.cuda.empty_cache()
 
 
+def bench_gemm4(iters):
+    """K4: fused NF4 GEMM (tcgen05) vs the reference's composition (dequantize_4bit + F.linear), BASELINE config 4."""
+    for (N, K) in [(14336, 4096), (4096, 14336)]:
+        W = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
+        q, st = F.quantize_4bit(W, blocksize=64, compress_statistics=False, quant_type="nf4")
+        del W
+        nbuf = 6                                   # 6 x 29 MB of packed weights + absmax > L2
+        qs = [q.clone() for _ in range(nbuf)]
+        for batch in (16, 32, 64, 128, 256):
+            x = torch.randn(batch, K, device="cuda").bfloat16()
+            outs = [torch.empty(batch, N, dtype=torch.bfloat16, device="cuda") for _ in range(nbuf)]
+            F.gemm_4bit(x, qs[0], st, out=outs[0])   # allocates the split-K workspace outside the capture
+            fns = [(lambda i=i: F.gemm_4bit(x, qs[i], st, out=outs[i])) for i in range(nbuf)]
+            us = time_graph(fns, iters)
+            nbytes = N * K // 2 + 4 * N * K // 64 + 2 * batch * (K + N)
+            flops = 2.0 * batch * N * K
+            fns = [(lambda i=i: torch.nn.functional.linear(x, F.dequantize_4bit(qs[i], st))) for i in range(nbuf)]
+            us_ref = time_graph(fns, max(2, iters // 2))
+            print(json.dumps({"kernel": f"gemm4_nf4_bf16_{N}x{K}_b{batch}", "us": round(us, 2), "GBps": round(nbytes / us / 1e3, 1),
+                              "hbm_frac": round(nbytes / us / 1e3 / PEAK_HBM, 4), "TFLOPs": round(flops / us / 1e6, 1),
+                              "bf16_frac": round(flops / us / 1e6 / PEAK_BF16, 4),
+                              "reference_composition_us": round(us_ref, 2), "speedup_vs_composition": round(us_ref / us, 2)}), flush=True)
+            del outs
+
+
 def bench_int8(iters):
     m, k, n = 4096, 4096, 16384
     A = torch.randn(m, k, device="cuda").half()
@@ -173,7 +198,7 @@ def bench_int8(iters):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="quant,gemv,int8")
+    ap.add_argument("--only", default="quant,gemv,gemm4,int8")
     ap.add_argument("--iters", type=int, default=20)
     a = ap.parse_args()
     torch.manual_seed(0)
@@ -182,5 +207,7 @@ if __name__ == "__main__":
         bench_quant(a.iters)
     if "gemv" in which:
         bench_gemv(a.iters)
+    if "gemm4" in which:
+        bench_gemm4(a.iters)
     if "int8" in which:
         bench_int8(a.iters)

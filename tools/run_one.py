@@ -28,6 +28,14 @@ elif what in ("quant", "dequant"):
         q, st = F.quantize_4bit(src[i % 4], blocksize=64, quant_type="nf4")
         if what == "dequant":
             F.dequantize_4bit(q, st)
+elif what == "gemm4":
+    N, K, batch = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    W = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
+    q, st = F.quantize_4bit(W, blocksize=64, compress_statistics=False, quant_type="nf4")
+    packs = [q.clone() for _ in range(4)]
+    x = torch.randn(batch, K, device="cuda").bfloat16()
+    for i in range(8):
+        y = F.gemm_4bit(x, packs[i % 4], st)
 elif what == "stats":
     A = [torch.randn(4096, 4096, device="cuda").half() for _ in range(4)]
     for i in range(8):
