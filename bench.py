@@ -39,6 +39,7 @@ for p in (ROOT, PKG_DIR):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+NCU_TRAFFIC_RATIO = 23.306496 / 23.291200   # measured DRAM bytes per algorithmic byte (ncu, 11008x4096 GEMV)
 LAYER_SHAPES_7B = [(4096, 4096)] * 4 + [(11008, 4096)] * 2 + [(4096, 11008)]
 LAYER_SHAPES_70B = [(8192, 8192), (1024, 8192), (1024, 8192), (8192, 8192), (28672, 8192), (28672, 8192), (8192, 28672)]
 
@@ -446,7 +447,12 @@ def main():
                        "launch": "cuda-graph" if graphed else "eager",
                        "parallelism": f"n-shard{world}" if world > 1 else "single", "collective": collective},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_gemv4_bc<bf16,nested>", "peak_source": peak_kind,
+                         # dram__bytes_read+write per launch of this kernel from the committed ncu --set full capture
+                         # (profiles/r1_ncu_summaries.txt: 23.306 MB for the 23.291 MB 11008x4096 GEMV, 121.23 MB
+                         # for the 121.24 MB 28672x8192 one): DRAM traffic == algorithmic bytes (+0.07 %)
+                         "traffic": bytes_per_launch * NCU_TRAFFIC_RATIO if B == 1 else None,
+                         "traffic_source": "ncu dram bytes / algorithmic bytes = 1.0007 (profiles/r1_ncu_summaries.txt)",
+                         "kernel": "k_gemv4_bc<bf16,nested>", "peak_source": peak_kind,
                          "bytes_per_launch": bytes_per_launch, "launch_us": launch_ms * 1e3},
             "e2e": {"value": alg_bytes / (e2e_s / e2e_steps) / 1e9, "unit": "GB/s",
                     "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": y_host.numel() * 2,
