@@ -465,258 +465,6 @@ __global__ void __launch_bounds__(kFastThreads, 1) k_gemv4_fast(const GemvArgs a
 }
 
 // ------------------------------------------------------------------------------------------------
-// TMA-staged, warp-specialised fast path (blocksize 64, K % 256 == 0).  One persistent CTA per SM:
-//   warp 16      : PRODUCER -- cp.async.bulk (TMA 1-D) copies of packed rows into a 3-stage shared-memory ring
-//                  per consumer group, completion on mbarriers (complete_tx); runs up to 3 stages
-//                  (48 KB per group) ahead of the consumers, so ~96 KB per SM is in flight towards HBM;
-//   warps 0..15  : CONSUMERS, two groups of 8 warps; a group owns one 16-row tile at a time, a stage is a
-//                  2048-element K slab of it (1 KB per row, one 256-element chunk per warp).
-// Rows are stored with a 1056-byte pitch so the 64-bit fragment reads are bank-conflict-free; the dequant
-// LUT, MMA and absmax handling are those of k_gemv4_fast.
-// ------------------------------------------------------------------------------------------------
-constexpr int kTmaGroups = 2;                           // consumer groups of 8 warps (3 x 2 stages measured slower)
-constexpr int kTmaConsumers = kTmaGroups * kGemvWarps;  // 16 warps
-constexpr int kTmaThreads = (kTmaConsumers + 1) * 32;   // 544
-constexpr int kTmaStages = 3;
-constexpr int kSlabK = 2048;                            // K elements per stage
-constexpr int kRowPitch = kSlabK / 2 + 32;              // 1056 B
-constexpr int kStageBytes = 16 * kRowPitch;             // 16896 B
-constexpr int kRingBytes = kTmaStages * kStageBytes;    // 50688 B
-constexpr int kTmaHead = 256 + 64 + 1024 + 192;         // barriers, codeT, code2, pad -> 1536 B
-constexpr int kTmaRedBytes = kTmaGroups * 2 * kGemvWarps * 128 * 4;    // 24 KB
-// region A (before the 64 KB-aligned table): head + ring of group 0; region B (after it): rings of groups 1.. + s_red
-constexpr int kTmaSmem = 65536 + 65536 + (kTmaGroups - 1) * kRingBytes + kTmaRedBytes;
-static_assert(kTmaHead + kRingBytes <= 65536 - 1024, "region A overflows");
-static_assert(kTmaSmem <= 227 * 1024, "too much shared memory");
-
-__device__ __forceinline__ uint2 lds_u64(uint32_t saddr) {
-  uint2 v;
-  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
-  return v;
-}
-__device__ __forceinline__ void mbar_init_(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx_(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  long long t0 = 0;
-  for (int spin = 0;; spin++) {
-    asm volatile("{\n .reg .pred P;\n mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n selp.u32 %0, 1, 0, P;\n}"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (done) return;
-    if (spin == 64) t0 = clock64();
-    if (spin > 64 && clock64() - t0 > 2000000000ll) __trap();   // protocol bug: fail, never hang
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-template <typename T, bool NESTED>
-__global__ void __launch_bounds__(kTmaThreads, 1) k_gemv4_tma(const GemvArgs a) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
-  const uint32_t lut_s = (smem_base + kTmaHead + kRingBytes + 0xFFFFu) & ~0xFFFFu;
-  if (lut_s + 65536u + (kTmaGroups - 1) * kRingBytes + kTmaRedBytes > smem_base + kTmaSmem) __trap();
-  // region A (before the table): barriers | codeT | code2 | ring of group 0
-  uint32_t *s_codeT = reinterpret_cast<uint32_t *>(smem + 256);
-  float *s_code2 = reinterpret_cast<float *>(smem + 256 + 64);
-  uint32_t ring_s[kTmaGroups];
-  ring_s[0] = smem_base + kTmaHead;
-#pragma unroll
-  for (int i = 1; i < kTmaGroups; i++) ring_s[i] = lut_s + 65536u + (i - 1) * kRingBytes;
-  unsigned char *s_lut = smem + (lut_s - smem_base);
-  float *s_red = reinterpret_cast<float *>(smem + (lut_s - smem_base) + 65536 + (kTmaGroups - 1) * kRingBytes);
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nchunks = a.K >> 8;
-  const int nslabs = (a.K + kSlabK - 1) / kSlabK;
-  const int kb = a.K >> 6;
-  const int ntiles = (a.N + 15) >> 4;
-  const int tile_stride = gridDim.x * kTmaGroups;
-  const uint32_t row_bytes = (uint32_t)(a.K >> 1);
-
-  if (tid == 0) {
-    for (int i = 0; i < kTmaGroups * kTmaStages; i++) {
-      mbar_init_(smem_base + i * 8, 1);                                       // full: producer's expect_tx arrival
-      mbar_init_(smem_base + (kTmaGroups * kTmaStages + i) * 8, kGemvWarps);  // empty: one arrival per consumer warp
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (NESTED && tid < 256) s_code2[tid] = a.code2[tid];
-  if (tid < 16) s_codeT[tid] = MmaT<T>::pack(a.code[tid], 0.0f) & 0xFFFFu;
-  __syncthreads();
-
-  if (warp == kTmaConsumers) {
-    // ===================== producer =====================
-    if (lane < 16) {
-      int n[kTmaGroups], tile[kTmaGroups], slab[kTmaGroups];
-#pragma unroll
-      for (int i = 0; i < kTmaGroups; i++) { n[i] = 0; slab[i] = 0; tile[i] = (int)blockIdx.x * kTmaGroups + i; }
-      bool any = true;
-      while (any) {
-        any = false;
-#pragma unroll
-        for (int grp = 0; grp < kTmaGroups; grp++) {
-          if (tile[grp] >= ntiles) continue;
-          any = true;
-          const int slot = n[grp] % kTmaStages;
-          const uint32_t parity = (uint32_t)(n[grp] / kTmaStages) & 1u;
-          const uint32_t full = smem_base + (grp * kTmaStages + slot) * 8;
-          const uint32_t empty = smem_base + (kTmaGroups * kTmaStages + grp * kTmaStages + slot) * 8;
-          mbar_wait_(empty, parity ^ 1u);
-          const uint32_t off = (uint32_t)slab[grp] * (kSlabK / 2);
-          const uint32_t bytes = min((uint32_t)(kSlabK / 2), row_bytes - off);
-          if (lane == 0) mbar_expect_tx_(full, 16u * bytes);
-          __syncwarp(0x0000ffffu);
-          const int row = min(tile[grp] * 16 + lane, a.N - 1);
-          bulk_g2s(ring_s[grp] + slot * kStageBytes + lane * kRowPitch, a.B + (size_t)row * row_bytes + off, bytes, full);
-          n[grp]++;
-          if (++slab[grp] == nslabs) { slab[grp] = 0; tile[grp] += tile_stride; }
-        }
-      }
-    }
-    return;
-  }
-
-  // ===================== consumers =====================
-  // build the byte LUT with all consumer threads, then a consumer-only barrier
-  {
-    const int j = tid & 7;
-    for (int e = tid >> 3; e < 256; e += kTmaConsumers * 4) {
-      const uint32_t v = s_codeT[e >> 4] | (s_codeT[e & 15] << 16);
-      *reinterpret_cast<uint4 *>(s_lut + e * 256 + j * 16) = make_uint4(v, v, v, v);
-    }
-  }
-  asm volatile("bar.sync %0, %1;" ::"r"(kTmaGroups + 1), "r"(kTmaConsumers * 32) : "memory");
-
-  const int grp = warp >> 3, gw = warp & 7, gtid = tid & 255;
-  const int g = lane >> 2, t = lane & 3;
-  const float offset = a.offset;
-  const int bs2_shift = a.bs2_shift;
-  const T *xrow = reinterpret_cast<const T *>(a.x) + (size_t)min(g, a.batch - 1) * a.K + t * 16;
-  const bool has_x = g < a.batch;
-  uint4 xa = make_uint4(0, 0, 0, 0), xb = make_uint4(0, 0, 0, 0);
-  const uint32_t lutlane = lut_s | (uint32_t)(lane * 4);
-  // this lane's fragment position inside a stage: rows g / g+8, its warp's 128-byte chunk, 8 bytes per step
-  const uint32_t frag_off = (uint32_t)g * kRowPitch + (uint32_t)gw * 128 + (uint32_t)t * 8;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  int parity_red = 0;
-  int n = 0;
-
-  // absmax of (tile, slab) for this warp's chunk, rows g and g+8 (registers, fetched one stage ahead)
-  struct Abs { uint32_t q[2]; float am2[2]; float4 am4[2]; };
-  auto load_abs = [&](Abs &ab, int tile, int slab) {
-    const int c = slab * (kSlabK / 256) + gw;
-    if (tile >= ntiles || c >= nchunks) return;
-    const int row_lo = min(tile * 16 + g, a.N - 1), row_hi = min(tile * 16 + g + 8, a.N - 1);
-    const size_t b0 = (size_t)row_lo * kb + c * 4, b1 = (size_t)row_hi * kb + c * 4;
-    if (NESTED) {
-      ab.q[0] = __ldg(reinterpret_cast<const uint32_t *>(a.qabsmax + b0));
-      ab.q[1] = __ldg(reinterpret_cast<const uint32_t *>(a.qabsmax + b1));
-      ab.am2[0] = __ldg(a.absmax2 + (b0 >> bs2_shift));
-      ab.am2[1] = __ldg(a.absmax2 + (b1 >> bs2_shift));
-    } else {
-      ab.am4[0] = __ldg(reinterpret_cast<const float4 *>(a.absmax + b0));
-      ab.am4[1] = __ldg(reinterpret_cast<const float4 *>(a.absmax + b1));
-    }
-  };
-
-  auto consume = [&](const Abs &ab, int slab, uint32_t stage_s) {
-    const int c = slab * (kSlabK / 256) + gw;
-    if (c >= nchunks) return;   // partial last slab: this warp has no chunk
-    float am[4][2];
-    if (NESTED) {
-#pragma unroll
-      for (int h = 0; h < 2; h++)
-#pragma unroll
-        for (int s = 0; s < 4; s++)
-          am[s][h] = __fadd_rn(__fmul_rn(s_code2[(ab.q[h] >> (8 * s)) & 0xFFu], ab.am2[h]), offset);
-    } else {
-#pragma unroll
-      for (int h = 0; h < 2; h++) { am[0][h] = ab.am4[h].x; am[1][h] = ab.am4[h].y; am[2][h] = ab.am4[h].z; am[3][h] = ab.am4[h].w; }
-    }
-    const uint4 *x4 = reinterpret_cast<const uint4 *>(xrow + (size_t)c * 256);
-    const uint32_t fs = stage_s + frag_off;
-#pragma unroll
-    for (int s = 0; s < 4; s++) {
-      if (has_x) { xa = __ldg(x4 + s * 8); xb = __ldg(x4 + s * 8 + 1); }
-      const uint32_t xr[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-      const uint2 w_lo = lds_u64(fs + s * 32), w_hi = lds_u64(fs + 8 * kRowPitch + s * 32);
-      const uint32_t wl[2] = {w_lo.x, w_lo.y};
-      const uint32_t wh[2] = {w_hi.x, w_hi.y};
-      float d[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const uint32_t src_l = wl[i >> 1], src_h = wh[i >> 1];
-        const uint32_t sel0 = (i & 1) ? 0x7624u : 0x7604u, sel1 = (i & 1) ? 0x7634u : 0x7614u;
-        uint32_t af[4];
-        af[0] = lds_u32(__byte_perm(src_l, lutlane, sel0));
-        af[2] = lds_u32(__byte_perm(src_l, lutlane, sel1));
-        af[1] = lds_u32(__byte_perm(src_h, lutlane, sel0));
-        af[3] = lds_u32(__byte_perm(src_h, lutlane, sel1));
-        MmaT<T>::mma(d, af, xr[2 * i], xr[2 * i + 1]);
-      }
-      acc[0] = __fmaf_rn(d[0], am[s][0], acc[0]);
-      acc[1] = __fmaf_rn(d[1], am[s][0], acc[1]);
-      acc[2] = __fmaf_rn(d[2], am[s][1], acc[2]);
-      acc[3] = __fmaf_rn(d[3], am[s][1], acc[3]);
-    }
-  };
-
-  auto finish_tile = [&](int done_tile) {
-    float *red = s_red + ((grp * 2 + parity_red) * kGemvWarps) * 128;
-    float *mine = red + gw * 128;
-    mine[g * 8 + 2 * t] = acc[0];
-    mine[g * 8 + 2 * t + 1] = acc[1];
-    mine[(g + 8) * 8 + 2 * t] = acc[2];
-    mine[(g + 8) * 8 + 2 * t + 1] = acc[3];
-    asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
-    if (gtid < 16 * a.batch) {
-      const int row = gtid & 15, col = gtid >> 4;
-      float sum = 0.f;
-#pragma unroll
-      for (int w = 0; w < kGemvWarps; w++) sum += red[w * 128 + row * 8 + col];
-      const int r = done_tile * 16 + row;
-      if (r < a.N) reinterpret_cast<T *>(a.out)[(size_t)col * a.N + r] = from_float<T>(sum);
-    }
-    parity_red ^= 1;
-    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-  };
-
-  int tile = blockIdx.x * kTmaGroups + grp, slab = 0;
-  Abs abA, abB;
-  load_abs(abA, tile, 0);
-  auto stage_step = [&](const Abs &cur, Abs &nxt) {
-    int nslab = slab + 1, ntile = tile;
-    if (nslab == nslabs) { nslab = 0; ntile = tile + tile_stride; }
-    load_abs(nxt, ntile, nslab);
-    const int slot = n % kTmaStages;
-    const uint32_t parity = (uint32_t)(n / kTmaStages) & 1u;
-    mbar_wait_(smem_base + (grp * kTmaStages + slot) * 8, parity);
-    consume(cur, slab, ring_s[grp] + slot * kStageBytes);
-    __syncwarp();
-    if (lane == 0) mbar_arrive_(smem_base + (kTmaGroups * kTmaStages + grp * kTmaStages + slot) * 8);
-    if (ntile != tile) finish_tile(tile);
-    n++;
-    tile = ntile;
-    slab = nslab;
-  };
-  while (tile < ntiles) {
-    stage_step(abA, abB);
-    if (tile >= ntiles) break;
-    stage_step(abB, abA);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Block-column path (batch 1, blocksize 64, K % 256 == 0): the headline kernel.
 //
 // The MMA's eight output columns are not wasted on a single activation row: column j of the 16x8
@@ -1396,16 +1144,7 @@ static void launch_mma_inst(const GemvArgs &a) {
     }
   }
   if (a.npeers > 0) { latch_error(cudaErrorInvalidValue, "gemv_4bit: peer outputs are only available in the block-column kernel"); return; }
-  if (VEC4 && !impl_reg && exp_mode == 0) {
-    static bool attr2[64] = {false};
-    if (!attr2[dev]) {
-      latch_error(cudaFuncSetAttribute(k_gemv4_tma<T, NESTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmem), "gemv tma smem attr");
-      attr2[dev] = true;
-    }
-    const int ctas = ceil_div(ceil_div(a.N, 16), kTmaGroups);
-    const int grid = ctas < num_sms[dev] ? ctas : num_sms[dev];
-    k_gemv4_tma<T, NESTED><<<grid, kTmaThreads, kTmaSmem, current_stream()>>>(a2);
-  } else if (VEC4) {
+  if (VEC4) {
     const int tiles = ceil_div(a.N, 16);
     const int ctas = ceil_div(tiles, kFastGroups);
     const int grid = ctas < num_sms[dev] ? ctas : num_sms[dev];
