@@ -81,6 +81,22 @@ class MatMul8bitLt(torch.autograd.Function):
         if A.dtype != torch.float16:
             warnings.warn(f"MatMul8bitLt: inputs will be cast from {A.dtype} to float16 during quantization")
 
+        # 0. inference fast path (additive): the whole forward in one native call, no host synchronisation.  Taken when
+        # nothing needs a gradient, the weight is already int8 row-major (CB / SCB) and threshold > 0.
+        if (F.FUSED_INT8_LINEAR and not any(ctx.needs_input_grad[:2]) and not state.has_fp16_weights and state.threshold > 0.0
+                and A.dtype == torch.float16 and state.SCB is not None and (bias is None or bias.dtype == torch.float16)):
+            CBrow = state.CB if state.CB is not None else (state.CxB if (state.SB and state.SB[1] == "row") else None)
+            if CBrow is not None and CBrow.dtype == torch.int8 and CBrow.dim() == 2:
+                fused = F.int8_linear_fused(A, CBrow, state.SCB, bias=bias, threshold=state.threshold)
+                if fused is not None:
+                    ctx.state = state
+                    ctx.formatB = formatB
+                    ctx.grad_shape = input_shape
+                    ctx.dtype_A, ctx.dtype_B, ctx.dtype_bias = A.dtype, B.dtype, None if bias is None else bias.dtype
+                    ctx.tensors = [None, None, None]
+                    ctx.tensor_states = (None, None)
+                    return fused
+
         # 1. quantise A (row- and column-wise int8 + outlier COO)
         if len(A.shape) == 3:
             A = A.reshape(-1, A.shape[-1])

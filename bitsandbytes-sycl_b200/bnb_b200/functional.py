@@ -25,6 +25,7 @@ dtype2bytes = {torch.float32: 4, torch.float16: 2, torch.bfloat16: 2, torch.uint
 
 # B200-native switches (additive; defaults pick the fast path, the reference-shaped path stays reachable)
 FUSED_NESTED_GEMV = os.environ.get("BNB_B200_FUSED_NESTED_GEMV", "1") != "0"
+FUSED_INT8_LINEAR = os.environ.get("BNB_B200_FUSED_INT8_LINEAR", "1") != "0"
 FUSED_GEMM_4BIT = os.environ.get("BNB_B200_FUSED_GEMM_4BIT", "1") != "0"
 INT8_LAYOUT = os.environ.get("BNB_B200_INT8_LAYOUT", "row")  # "row" (native) | "col_turing" | "col_ampere"
 
@@ -805,6 +806,57 @@ def int8_linear_dequant(CA: Tensor, CB: Tensor, SCA: Tensor, SCB: Tensor, bias: 
     post_call(prev)
     if rc != 0:
         raise Exception("cublasLt ran into an error!")
+    return out
+
+
+_INT8_WS: Dict[Any, Any] = {}
+
+
+def int8_linear_fused(A: Tensor, CB: Tensor, SCB: Tensor, bias: Optional[Tensor] = None, threshold: float = 6.0,
+                      out: Optional[Tensor] = None, return_quantized: bool = False):
+    """ADDITIVE: the whole LLM.int8 inference forward (MatMul8bitLt.forward, reference _functions.py:292-434, with
+    has_fp16_weights=False and threshold > 0) in one native call: no host synchronisation, no torch.unique / sort /
+    index kernels.  A fp16 [m, k]; CB int8 [n, k] row-major; SCB fp32 [n].  Returns out fp16 [m, n], or None when
+    the native path does not take the shape (the caller then runs the step-by-step route).  With
+    return_quantized=True also returns (CA, SCA, idx, count): quantised activations (outlier columns zeroed), row
+    statistics, ascending outlier column list and its device-side length."""
+    if A.dtype != torch.float16 or CB.dtype != torch.int8 or threshold <= 0.0:
+        return None
+    A2 = A.reshape(-1, A.shape[-1]).contiguous()
+    m, k = A2.shape
+    n = CB.shape[0]
+    if k % 16 != 0 or CB.shape[1] != k or not CB.is_contiguous():
+        return None
+    key = (A.device, m, n, k)
+    ws = _INT8_WS.get(key)
+    if ws is None:
+        dev = A.device
+        ws = dict(CA=torch.empty((m, k), dtype=torch.int8, device=dev), SCA=torch.empty(m, dtype=torch.float32, device=dev),
+                  colflag=torch.empty(k, dtype=torch.uint8, device=dev), pos=torch.empty(k, dtype=torch.int16, device=dev),
+                  idx=torch.zeros(max(k, 16), dtype=torch.int32, device=dev), count=torch.zeros(1, dtype=torch.int32, device=dev),
+                  subA=torch.empty((m, 16), dtype=torch.float16, device=dev), subB=torch.empty((n, 16), dtype=torch.float16, device=dev))
+        if len(_INT8_WS) > 8:
+            _INT8_WS.clear()
+        _INT8_WS[key] = ws
+    if bias is not None and bias.dtype != torch.float16:
+        return None
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float16, device=A.device)
+    SCB32 = SCB if SCB.dtype == torch.float32 else SCB.float()
+    prev = pre_call(A.device)
+    is_on_gpu([A2, CB, SCB32, bias, out])
+    rc = lib.cint8_linear_fp16(get_ptr(A2), get_ptr(CB), get_ptr(SCB32), get_ptr(bias), get_ptr(out), ct.c_float(threshold),
+                               ct.c_int32(m), ct.c_int32(n), ct.c_int32(k), get_ptr(ws["CA"]), get_ptr(ws["SCA"]),
+                               get_ptr(ws["colflag"]), get_ptr(ws["pos"]), get_ptr(ws["idx"]), ct.c_int32(ws["idx"].numel()),
+                               get_ptr(ws["count"]), get_ptr(ws["subA"]), get_ptr(ws["subB"]))
+    post_call(prev)
+    if rc == 1:
+        return None
+    if rc != 0:
+        raise Exception("cublasLt ran into an error!")
+    out = out.reshape(*A.shape[:-1], n)
+    if return_quantized:
+        return out, ws["CA"], ws["SCA"], ws["idx"], ws["count"]
     return out
 
 

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "bnb_b200")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB = os.path.join(OUT_DIR, "libbitsandbytes_b200.so")
-SOURCES = ["c_api.cu", "quant_blockwise.cu", "gemv_4bit.cu", "gemm_4bit.cu", "int8_quant.cu", "igemm.cu"]
+SOURCES = ["c_api.cu", "quant_blockwise.cu", "gemv_4bit.cu", "gemm_4bit.cu", "int8_quant.cu", "int8_fused.cu", "igemm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -41,6 +41,7 @@ void dequant_mm_int32_fp16(const int *, const float *, const float *, __half *, 
 int igemmlt(int, int, bool, int, int, int, const signed char *, const signed char *, void *, const float *, int, int, int);
 int igemm_rowmajor_32(int, int, int, const signed char *, const signed char *, int *);
 int igemm_rowmajor_dequant_fp16(int, int, int, const signed char *, const signed char *, const float *, const float *, const __half *, __half *);
+int int8_linear_fused(const __half *, const signed char *, const float *, const __half *, __half *, float, int, int, int, signed char *, float *, unsigned char *, short *, int *, int, int *, __half *, __half *);
 
 }  // namespace bnb
 
@@ -140,6 +141,11 @@ void cextractOutliers_ampere(char *A, int *idx, char *out, int idx_size, int row
 int cigemm_rowmajor_32(int m, int n, int k, const int8_t *A, const int8_t *B, int *C) { return igemm_rowmajor_32(m, n, k, A, B, C); }
 int cigemm_rowmajor_dequant_fp16(int m, int n, int k, const int8_t *A, const int8_t *B, float *rowStats, float *colStats, void *bias, void *out) {
   return igemm_rowmajor_dequant_fp16(m, n, k, A, B, rowStats, colStats, (half_t *)bias, (half_t *)out); }
+
+int cint8_linear_fp16(void *A, const int8_t *CB, float *SCB, void *bias, void *out, float threshold, int m, int n, int k,
+                      int8_t *CA, float *SCA, unsigned char *colflag, short *pos, int *idx, int idx_cap, int *count, void *subA, void *subB) {
+  return int8_linear_fused((half_t *)A, CB, SCB, (half_t *)bias, (half_t *)out, threshold, m, n, k, CA, SCA, colflag, pos, idx,
+                           idx_cap, count, (half_t *)subA, (half_t *)subB); }
 
 // ---------------------------------------------------------------- context (pythonInterface.cpp:295)
 struct Context { int device; };

@@ -69,7 +69,8 @@ constexpr int kStages = 4;
 constexpr int kStageA = BM * BK, kStageB = BN * BK, kStageBytes = kStageA + kStageB;  // 16 KB + 32 KB
 constexpr int kIgemmThreads = 192;
 constexpr int kTmemCols = 512;
-constexpr int kIgemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * (4 + 2) /*col stats + bias*/;
+constexpr int kIgemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * (4 + 2) /*col stats + bias*/ +
+                           2 * BN * 8 * 4 /*outlier columns of the weight as fp32, per accumulator buffer*/;
 
 enum { EPI_INT32 = 0, EPI_DEQUANT_FP16 = 1 };
 
@@ -80,6 +81,10 @@ struct IgemmArgs {
   const float *colStats;
   const __half *bias;      // may be null
   __half *out;             // row-major [M,N]
+  // 16-bit outlier product folded into the dequant epilogue (int8_fused.cu): out = half(half(dequant) + half(sum_o subA*subB))
+  const __half *subA;      // [M,16] (null: none)
+  const __half *subB;      // [N,16]
+  const int *nout;         // device-side number of outlier columns
 };
 
 template <int EPI>
@@ -92,6 +97,7 @@ k_igemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
   float *s_cs = reinterpret_cast<float *>(smem + kStages * kStageBytes + 256);  // [2][BN]
   __half *s_bias = reinterpret_cast<__half *>(s_cs + 2 * BN);                   // [2][BN]
+  float4 *s_sb = reinterpret_cast<float4 *>(s_bias + 2 * BN);                   // [2][BN][8 floats] = 2 float4 per column
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (a.M + BM - 1) / BM, num_n = (a.N + BN - 1) / BN;
@@ -164,6 +170,10 @@ k_igemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int acc = it & 1; const uint32_t use = (uint32_t)(it >> 1);
       const int row = m_blk * BM + q * 32 + lane;
       float rs = 0.f;
+      float arow[8];
+      int nout = 0;
+#pragma unroll
+      for (int o = 0; o < 8; o++) arow[o] = 0.f;
       if (EPI == EPI_DEQUANT_FP16) {
         // stage this tile's column stats / bias; the buffer `acc` was last read two tiles ago
         for (int j = et; j < BN; j += 128) {
@@ -172,6 +182,30 @@ k_igemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           s_bias[acc * BN + j] = (a.bias != nullptr && col < a.N) ? a.bias[col] : __float2half(0.f);
         }
         rs = row < a.M ? a.rowStats[row] : 0.f;
+        if (a.subA != nullptr) {
+          nout = *a.nout;
+          if (nout > 8) nout = 0;   // more than 8 outlier columns: k_i8_outlier_tail adds the whole product instead
+          if (nout > 0) {
+            for (int j = et; j < BN; j += 128) {
+              const int col = n_blk * BN + j;
+              float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              if (col < a.N) {
+                const uint4 b = __ldg(reinterpret_cast<const uint4 *>(a.subB + (size_t)col * 16));
+                const __half *hb = reinterpret_cast<const __half *>(&b);
+#pragma unroll
+                for (int o = 0; o < 8; o++) f[o] = __half2float(hb[o]);
+              }
+              s_sb[(acc * BN + j) * 2] = make_float4(f[0], f[1], f[2], f[3]);
+              s_sb[(acc * BN + j) * 2 + 1] = make_float4(f[4], f[5], f[6], f[7]);
+            }
+            if (row < a.M) {
+              const uint4 a0 = __ldg(reinterpret_cast<const uint4 *>(a.subA + (size_t)row * 16));
+              const __half *h0 = reinterpret_cast<const __half *>(&a0);
+#pragma unroll
+              for (int o = 0; o < 8; o++) arow[o] = __half2float(h0[o]);
+            }
+          }
+        }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       tc::mbar_wait(tc::smem_u32(tfull + acc), use & 1);
@@ -204,6 +238,21 @@ k_igemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               t = __fmul_rn(t, s_cs[acc * BN + c * 32 + j]);
               t = __fadd_rn(t, __half2float(s_bias[acc * BN + c * 32 + j]));
               h[j] = __float2half_rn(t);
+              if (nout > 0) {   // + the 16-bit product over the first 8 outlier columns (warp-uniform branch, broadcast smem reads)
+                const float4 b0 = s_sb[(acc * BN + c * 32 + j) * 2];
+                float u = __fmul_rn(arow[0], b0.x);
+                u = __fmaf_rn(arow[1], b0.y, u);
+                u = __fmaf_rn(arow[2], b0.z, u);
+                u = __fmaf_rn(arow[3], b0.w, u);
+                if (nout > 4) {
+                  const float4 b1 = s_sb[(acc * BN + c * 32 + j) * 2 + 1];
+                  u = __fmaf_rn(arow[4], b1.x, u);
+                  u = __fmaf_rn(arow[5], b1.y, u);
+                  u = __fmaf_rn(arow[6], b1.z, u);
+                  u = __fmaf_rn(arow[7], b1.w, u);
+                }
+                h[j] = __float2half_rn(__fadd_rn(__half2float(h[j]), __half2float(__float2half_rn(u))));
+              }
             }
             __half *dst = a.out + (long)row * a.N + col0;
             if (col0 + 32 <= a.N && (a.N & 7) == 0) {
@@ -323,6 +372,16 @@ int igemm_rowmajor_dequant_fp16(int m, int n, int k, const signed char *A, const
                                 const float *colStats, const __half *bias, __half *out) {
   IgemmArgs a{};
   a.M = m; a.N = n; a.K = k; a.rowStats = rowStats; a.colStats = colStats; a.bias = bias; a.out = out;
+  return igemm_rowmajor<EPI_DEQUANT_FP16>(A, B, a);
+}
+
+int igemm_rowmajor_dequant_outliers_fp16(int m, int n, int k, const signed char *A, const signed char *B, const float *rowStats,
+                                         const float *colStats, const __half *bias, __half *out, const __half *subA,
+                                         const __half *subB, const int *count) {
+  IgemmArgs a{};
+  a.M = m; a.N = n; a.K = k; a.rowStats = rowStats; a.colStats = colStats; a.bias = bias; a.out = out;
+  a.subA = subA; a.subB = subB; a.nout = count;
+  if ((k % 16) != 0 || (reinterpret_cast<uintptr_t>(A) % 16) != 0 || (reinterpret_cast<uintptr_t>(B) % 16) != 0) return 1;  // tcgen05 path only
   return igemm_rowmajor<EPI_DEQUANT_FP16>(A, B, a);
 }
 

@@ -225,3 +225,67 @@ def test_config3_full_size_checksum(F):
     assert torch.equal(col_sum, (B.double() @ As).long())
     slab = orc.igemm_rowmajor(A[1000:1016].cpu().numpy(), B[5000:5128].cpu().numpy())
     assert np.array_equal(C[1000:1016, 5000:5128].cpu().numpy(), slab)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused LLM.int8 inference forward (additive cint8_linear_fp16) vs the step-by-step reference orchestration
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_outlier_cols", [0, 3, 16, 23])
+@pytest.mark.parametrize("with_bias", [False, True])
+def test_int8_linear_fused_matches_stepwise(F, n_outlier_cols, with_bias):
+    """Same quantised activations / row statistics (bit-exact) and the same fp16 output (<= 2 ulp: only the fp32
+    summation order of the tiny outlier product differs, and that product is rounded to fp16 before it is added) as double_quant -> zero outlier columns -> int8 GEMM ->
+    mm_dequant -> + subA @ subB (reference autograd/_functions.py:292-434)."""
+    import bnb_b200
+    torch.manual_seed(100 + n_outlier_cols)
+    m, k, n = 200, 1024, 384
+    A = torch.randn(m, k, device="cuda").half()
+    cols = torch.randperm(k)[:n_outlier_cols].sort().values
+    for c in cols.tolist():          # an outlier column: a few rows at +-8, the rest ordinary (as in real activations)
+        rows = torch.randperm(m)[: max(1, m // 7)]
+        A[rows.cuda(), c] = 8.0 * (1 if c % 2 else -1)
+    lin = bnb_b200.nn.Linear8bitLt(k, n, bias=with_bias, has_fp16_weights=False, threshold=6.0).cuda().half()
+    with torch.no_grad():
+        old = F.FUSED_INT8_LINEAR
+        try:
+            F.FUSED_INT8_LINEAR = False
+            y_step = lin(A)
+            F.FUSED_INT8_LINEAR = True
+            CB = lin.state.CB if lin.state.CB is not None else lin.state.CxB
+            res = F.int8_linear_fused(A, CB, lin.state.SCB, bias=lin.bias, threshold=6.0, return_quantized=True)
+            assert res is not None
+            y_fused, CA, SCA, idx, count = res
+            y_mod = lin(A)                       # the module takes the fused path too
+        finally:
+            F.FUSED_INT8_LINEAR = old
+    torch.cuda.synchronize()
+    assert int(count.item()) == n_outlier_cols
+    assert torch.equal(idx[:n_outlier_cols].cpu().long(), cols)
+    CA_ref, _, SCA_ref, _, coo = F.double_quant(A, threshold=6.0)
+    CA_ref[:, cols.cuda()] = 0
+    assert torch.equal(SCA, SCA_ref)
+    assert torch.equal(CA, CA_ref)
+    assert torch.equal(y_fused, y_mod)
+    d = (y_fused.float() - y_step.float()).abs()
+    # the outlier product U is rounded to fp16 before it is added: a different fp32 summation order can move half(U) by
+    # one ulp OF U, which is more than an ulp of the result where the two terms cancel -> scale the ulp by max(|y|, |U|)
+    U = (A[:, cols.cuda()].float() @ (CB[:, cols.cuda()].float() * lin.state.SCB.float().view(-1, 1) / 127.0).half().float().t()).abs()
+    ulp = torch.maximum(torch.maximum(y_step.float().abs(), U), torch.tensor(2.0 ** -14, device="cuda")) * 2.0 ** -10
+    assert bool((d <= 2.01 * ulp).all()), float((d / ulp).max())
+    assert float((d > 0).float().mean()) < 0.02   # and almost everywhere bit-identical
+
+
+def test_int8_linear_fused_exact_vs_oracle(F):
+    """int32 accumulators are exact and the dequant chain is the oracle's: without outliers the fused output is
+    bit-identical to oracle mm_dequant(igemm(CA, CB))."""
+    torch.manual_seed(5)
+    m, k, n = 96, 512, 256
+    A = (torch.randn(m, k) * 0.5).half()
+    W = (torch.randn(n, k) * 0.05).half()
+    CB, _, SCB, _, _ = F.double_quant(W.cuda())
+    bias = torch.randn(n).half()
+    y, CA, SCA, idx, count = F.int8_linear_fused(A.cuda(), CB, SCB, bias=bias.cuda(), threshold=6.0, return_quantized=True)
+    assert int(count.item()) == 0
+    acc = orc.igemm_rowmajor(CA.cpu().numpy(), CB.cpu().numpy())
+    ref = orc.mm_dequant(acc, SCA.cpu().numpy(), SCB.cpu().numpy(), m, n, bias.view(torch.int16).numpy().view(np.uint16), col32=False)
+    assert np.array_equal(y.cpu().view(torch.int16).numpy().view(np.uint16), ref.view(np.uint16))
