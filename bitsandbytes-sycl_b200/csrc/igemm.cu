@@ -67,9 +67,10 @@ bool make_tmap_2d(CUtensorMap *map, const void *base, int elem_bytes, uint64_t r
 constexpr int BM = 128, BN = 256, BK = 128;  // BK in bytes == int8 elements
 constexpr int kStages = 4;
 constexpr int kStageA = BM * BK, kStageB = BN * BK, kStageBytes = kStageA + kStageB;  // 16 KB + 32 KB
-constexpr int kIgemmThreads = 192;
+constexpr int kEpiThreads = 256;                 // 8 epilogue warps: two per TMEM lane quarter, each takes half the columns
+constexpr int kIgemmThreads = 64 + kEpiThreads;
 constexpr int kTmemCols = 512;
-constexpr int kIgemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * (4 + 2) /*col stats + bias*/ +
+constexpr int kIgemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * (4 + 4) /*col stats + bias (fp32)*/ +
                            2 * BN * 8 * 4 /*outlier columns of the weight as fp32, per accumulator buffer*/;
 
 enum { EPI_INT32 = 0, EPI_DEQUANT_FP16 = 1 };
@@ -96,7 +97,7 @@ k_igemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t *full = bars, *empty = bars + kStages, *tfull = bars + 2 * kStages, *tempty = bars + 2 * kStages + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
   float *s_cs = reinterpret_cast<float *>(smem + kStages * kStageBytes + 256);  // [2][BN]
-  __half *s_bias = reinterpret_cast<__half *>(s_cs + 2 * BN);                   // [2][BN]
+  float *s_bias = s_cs + 2 * BN;                                                // [2][BN]
   float4 *s_sb = reinterpret_cast<float4 *>(s_bias + 2 * BN);                   // [2][BN][8 floats] = 2 float4 per column
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -107,7 +108,7 @@ k_igemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < kStages; s++) { tc::mbar_init(tc::smem_u32(full + s), 1); tc::mbar_init(tc::smem_u32(empty + s), 1); }
-      for (int i = 0; i < 2; i++) { tc::mbar_init(tc::smem_u32(tfull + i), 1); tc::mbar_init(tc::smem_u32(tempty + i), 4); }
+      for (int i = 0; i < 2; i++) { tc::mbar_init(tc::smem_u32(tfull + i), 1); tc::mbar_init(tc::smem_u32(tempty + i), kEpiThreads / 32); }
       tc::fence_barrier_init();
     }
     __syncwarp();
@@ -161,9 +162,10 @@ k_igemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else {
-    // ================= epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =================
+    // ================= epilogue (warps 2..9: TMEM lane quarter = warp & 3, column half = (warp - 2) >> 2) =================
     const int q = warp & 3;
-    const int et = threadIdx.x - 64;  // 0..127
+    const int half_n = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;  // 0..255
     int it = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
       const int m_blk = tile % num_m, n_blk = tile / num_m;
@@ -176,17 +178,17 @@ k_igemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int o = 0; o < 8; o++) arow[o] = 0.f;
       if (EPI == EPI_DEQUANT_FP16) {
         // stage this tile's column stats / bias; the buffer `acc` was last read two tiles ago
-        for (int j = et; j < BN; j += 128) {
+        for (int j = et; j < BN; j += kEpiThreads) {
           const int col = n_blk * BN + j;
           s_cs[acc * BN + j] = col < a.N ? a.colStats[col] : 0.f;
-          s_bias[acc * BN + j] = (a.bias != nullptr && col < a.N) ? a.bias[col] : __float2half(0.f);
+          s_bias[acc * BN + j] = (a.bias != nullptr && col < a.N) ? __half2float(a.bias[col]) : 0.f;
         }
         rs = row < a.M ? a.rowStats[row] : 0.f;
         if (a.subA != nullptr) {
           nout = *a.nout;
           if (nout > 8) nout = 0;   // more than 8 outlier columns: k_i8_outlier_tail adds the whole product instead
           if (nout > 0) {
-            for (int j = et; j < BN; j += 128) {
+            for (int j = et; j < BN; j += kEpiThreads) {
               const int col = n_blk * BN + j;
               float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
               if (col < a.N) {
@@ -206,17 +208,18 @@ k_igemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       }
       tc::mbar_wait(tc::smem_u32(tfull + acc), use & 1);
       tc::fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half_n * (BN / 2);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; c++) {
+      for (int c = 0; c < BN / 64; c++) {
         uint32_t v[32];
         tc::tmem_ld_32x32b_x32(taddr + c * 32, v);
         tc::tmem_ld_wait();
-        const int col0 = n_blk * BN + c * 32;
+        const int cl = half_n * (BN / 2) + c * 32;   // column inside the tile
+        const int col0 = n_blk * BN + cl;
         if (row < a.M && col0 < a.N) {
           if (EPI == EPI_INT32) {
             int *dst = a.C + (long)row * a.N + col0;
@@ -231,27 +234,42 @@ k_igemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           } else {
             __half h[32];
+            const float *cs = s_cs + acc * BN + cl, *sb = s_bias + acc * BN + cl;
+            // 32 independent chains, no branch inside: the single warp of a scheduler hides latency with ILP
 #pragma unroll
             for (int j = 0; j < 32; j++) {
               float t = __fmul_rn(__int2float_rn((int)v[j]), 6.200012e-05f);
               t = __fmul_rn(t, rs);
-              t = __fmul_rn(t, s_cs[acc * BN + c * 32 + j]);
-              t = __fadd_rn(t, __half2float(s_bias[acc * BN + c * 32 + j]));
+              t = __fmul_rn(t, cs[j]);
+              t = __fadd_rn(t, sb[j]);
               h[j] = __float2half_rn(t);
-              if (nout > 0) {   // + the 16-bit product over the first 8 outlier columns (warp-uniform branch, broadcast smem reads)
-                const float4 b0 = s_sb[(acc * BN + c * 32 + j) * 2];
-                float u = __fmul_rn(arow[0], b0.x);
-                u = __fmaf_rn(arow[1], b0.y, u);
-                u = __fmaf_rn(arow[2], b0.z, u);
-                u = __fmaf_rn(arow[3], b0.w, u);
-                if (nout > 4) {
-                  const float4 b1 = s_sb[(acc * BN + c * 32 + j) * 2 + 1];
+            }
+            if (nout > 0) {   // + the 16-bit product over the outlier columns (warp-uniform branches, broadcast smem reads)
+              const float4 *b = s_sb + (acc * BN + cl) * 2;
+              if (nout <= 4) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                  const float4 b0 = b[2 * j];
+                  float u = __fmul_rn(arow[0], b0.x);
+                  u = __fmaf_rn(arow[1], b0.y, u);
+                  u = __fmaf_rn(arow[2], b0.z, u);
+                  u = __fmaf_rn(arow[3], b0.w, u);
+                  h[j] = __float2half_rn(__fadd_rn(__half2float(h[j]), __half2float(__float2half_rn(u))));
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                  const float4 b0 = b[2 * j], b1 = b[2 * j + 1];
+                  float u = __fmul_rn(arow[0], b0.x);
+                  u = __fmaf_rn(arow[1], b0.y, u);
+                  u = __fmaf_rn(arow[2], b0.z, u);
+                  u = __fmaf_rn(arow[3], b0.w, u);
                   u = __fmaf_rn(arow[4], b1.x, u);
                   u = __fmaf_rn(arow[5], b1.y, u);
                   u = __fmaf_rn(arow[6], b1.z, u);
                   u = __fmaf_rn(arow[7], b1.w, u);
+                  h[j] = __float2half_rn(__fadd_rn(__half2float(h[j]), __half2float(__float2half_rn(u))));
                 }
-                h[j] = __float2half_rn(__fadd_rn(__half2float(h[j]), __half2float(__float2half_rn(u))));
               }
             }
             __half *dst = a.out + (long)row * a.N + col0;
