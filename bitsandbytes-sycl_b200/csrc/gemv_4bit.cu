@@ -976,6 +976,275 @@ k_gemv4_bct(const GemvArgs a, const __grid_constant__ CUtensorMap tmapB, int x_b
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMEM-staged block-column kernel: the packed weights never touch the LSU / L1TEX pipe.
+//
+// What bounds the block-column kernels above is the LSU data pipe (one 128-byte wavefront per clock per SM): the byte
+// LUT needs 128 wavefronts per 4 KB item, bringing the item into registers with LDG (or TMA + LDS) costs another
+// 32-50, the x fragments 32 and the scattered absmax loads ~20.  Here
+//   * the weights travel  HBM --TMA--> shared memory --tcgen05.cp--> TMEM --tcgen05.ld--> registers: three asynchronous
+//     engines, none of which uses an LSU wavefront, with a 256 KB TMEM ring (16 slots of 128 lanes x 32 columns) in
+//     front of the compute warps instead of a register ring;
+//   * a lane holds 16-BYTE pieces (half a quantisation block), so the lanes that feed x into one MMA sequence sit
+//     in ONE quarter-warp and their LDS.128 is a single wavefront (16 per item instead of 32);
+//   * the nested absmax bytes of the CTA's whole row range are copied to shared memory once, in the prologue.
+//
+// Stage = one 16-row tile x 1024 bytes of every row (8 half-chunks of 128 B = 2048 K elements) = 16 KB = four 4 KB
+// slots; slot q (TMEM lane quarter q, compute warp w with w % 4 == q) = half-chunks hc0+q and hc0+q+4.  The stage is
+// stored as eight planes p = (row half h, half-chunk jh, 64-byte piece jl) of [q][g][64 B] = 128 x 16 B: plane p is one
+// TMA box {64 B, 8 rows, 4 half-chunks} and one tcgen05.cp.128x128b (no swizzle, core matrix = 8 lanes x 16 B) into
+// TMEM columns [4p, 4p+4).  Lane (g,t) of slot q then owns, for rows g and g+8, the 16-byte pieces t of the four
+// 64-byte runs j = (jh, jl) of its slot: quantisation blocks 2j (t < 2) and 2j+1 (t >= 2) of the slot.
+//
+//   warp CW   (1 thread): TMA producer (weights are constants: runs ahead of griddepcontrol.wait)
+//   warp CW+1 (1 thread): TMEM owner + copier; tcgen05.commit frees the shared-memory stage and publishes the TMEM slot
+//   warps 0..CW-1       : compute; warp group w / 4 takes stages n = group (mod CW/4)
+// Arithmetic = k_gemv4_bc: one fp32 accumulator fragment runs through the 32 MMAs of an item; sequence j puts block 2j
+// in column 2j and block 2j+1 in column 2j+1, so afterwards lane (g,t) owns D[g | g+8][2t | 2t+1] = four distinct
+// (row, block) partial sums and applies the fp32 absmax once.  Same LUT, same exactness argument.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTmStage = 16384;                    // 8 planes x 2 KB
+constexpr int kTmBars = 65536;                     // sfull[8] | sempty[8] | tfull[16] | tempty[16] | tmem slot
+constexpr int kTmCode2 = 65536 + 1024;
+constexpr int kTmRing = 65536 + 2048;
+constexpr int kTmSlots = 16;                       // TMEM ring: 512 columns / 32
+constexpr int kTmMaxStages = 8;
+constexpr int kTmXPitch = 80;                      // bytes per 32-element piece of x in shared memory (64 + 16: conflict-free)
+
+// K-major, no swizzle, one 16-byte core-matrix column: 8-row groups 128 B apart
+__device__ __forceinline__ uint64_t tm_desc_nosw(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(128u >> 4) << 16;                // leading byte offset (not used: a single core matrix along K)
+  d |= (uint64_t)(128u >> 4) << 32;                // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void tmem_cp_128x128b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x128b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap *m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+template <typename T, bool NESTED, int CW>
+__global__ void __launch_bounds__((CW + 2) * 32, 1)
+k_gemv4_tm(const GemvArgs a, const __grid_constant__ CUtensorMap tmapB, int x_pieces_padded, int tiles_total, int nsmem, int abs_bytes) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  unsigned char *smem = smem_raw + (((raw_s + 1023u) & ~1023u) - raw_s);
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t sfull = smem_base + kTmBars, sempty = sfull + 64, tfull = sfull + 128, tempty = sfull + 256;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kTmBars + 384);
+  float *s_code2 = reinterpret_cast<float *>(smem + kTmCode2);
+  const uint32_t ring_s = smem_base + kTmRing;
+  unsigned char *s_x = smem + kTmRing + nsmem * kTmStage;
+  unsigned char *s_abs = s_x + (size_t)x_pieces_padded * kTmXPitch;                 // nested: qabsmax bytes of this CTA's rows
+  float *s_part = reinterpret_cast<float *>(s_abs + abs_bytes);                     // [tile_local][warp][16]
+  constexpr int G = CW / 4;
+  constexpr int CT = CW * 32;
+  asm volatile("griddepcontrol.launch_dependents;");
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kb = a.K >> 6;                   // blocks per row
+  const int nhc = a.K >> 8;                  // 128-byte half-chunks per row
+  const int spt = (nhc + 7) >> 3;            // stages per tile
+  const int t_begin = (int)((long)blockIdx.x * tiles_total / gridDim.x);
+  const int t_end = (int)((long)(blockIdx.x + 1) * tiles_total / gridDim.x);
+  const int ntl = t_end - t_begin;
+  const int nstages = ntl * spt;
+
+  if (tid == CW * 32) {
+    tc::prefetch_tmap(&tmapB);
+    for (int i = 0; i < kTmMaxStages; i++) { tc::mbar_init(sfull + i * 8, 1); tc::mbar_init(sempty + i * 8, 1); }
+    for (int i = 0; i < kTmSlots; i++) { tc::mbar_init(tfull + i * 8, 1); tc::mbar_init(tempty + i * 8, 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == CW + 1) tc::tmem_alloc(tc::smem_u32(tmem_slot), 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == CW) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int tl = 0, si = 0;
+      for (int n = 0; n < nstages; n++) {
+        const int st = n % nsmem;
+        tc::mbar_wait(sempty + st * 8, ((uint32_t)(n / nsmem) & 1u) ^ 1u);
+        tc::mbar_arrive_expect_tx(sfull + st * 8, kTmStage);
+        const uint32_t dst = ring_s + st * kTmStage;
+#pragma unroll
+        for (int p = 0; p < 8; p++)   // plane p = (h, jh, jl)
+          tma_load_4d(dst + p * 2048, &tmapB, sfull + st * 8, 64 * (p & 1), 8 * (p >> 2), si * 8 + 4 * ((p >> 1) & 1), t_begin + tl);
+        if (++si == spt) { si = 0; tl++; }
+      }
+    }
+  } else if (warp == CW + 1) {
+    // ================= copier: shared memory -> TMEM =================
+    if (lane == 0) {
+      for (int n = 0; n < nstages; n++) {
+        const int st = n % nsmem, sl = n % kTmSlots;
+        tc::mbar_wait(sfull + st * 8, (uint32_t)(n / nsmem) & 1u);
+        tc::mbar_wait(tempty + sl * 8, ((uint32_t)(n / kTmSlots) & 1u) ^ 1u);
+        tc::fence_after_sync();
+        const uint32_t src = ring_s + st * kTmStage;
+#pragma unroll
+        for (int p = 0; p < 8; p++) tmem_cp_128x128b(tmem_base + sl * 32 + p * 4, tm_desc_nosw(src + p * 2048));
+        tc::umma_commit(sempty + st * 8);
+        tc::umma_commit(tfull + sl * 8);
+      }
+    }
+  } else {
+    // ================= compute warps =================
+    const int g = lane >> 2, t = lane & 3;
+    const int q = warp & 3, grp = warp >> 2;
+    // ---- prologue: tables, absmax bytes, partial-sum slots (constants only), then the activations (after the dependency wait)
+    {
+      for (int i = tid; i < 256; i += CT) if (NESTED) s_code2[i] = __ldg(a.code2 + i);
+      const int j = tid & 7;
+      for (int e = tid >> 3; e < 256; e += CT / 8) {
+        const uint32_t v = (MmaT<T>::pack(__ldg(a.code + (e >> 4)), 0.0f) & 0xFFFFu) | (MmaT<T>::pack(__ldg(a.code + (e & 15)), 0.0f) << 16);
+        *reinterpret_cast<uint4 *>(smem + e * 256 + j * 16) = make_uint4(v, v, v, v);
+      }
+      if (NESTED) {
+        const size_t first = (size_t)t_begin * 16 * kb, total = (size_t)a.N * kb;
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.qabsmax + first);
+        for (int i = tid; i < abs_bytes / 16; i += CT)
+          if (first + (size_t)i * 16 + 16 <= total) *reinterpret_cast<uint4 *>(s_abs + i * 16) = __ldg(src + i);
+      }
+      for (int i = tid; i < ntl * CW * 16; i += CT) s_part[i] = 0.f;
+      asm volatile("griddepcontrol.wait;" ::: "memory");     // x (and out) belong to the previous kernel until here
+      // x in shared memory: 32-element pieces at a pitch of 80 B (four consecutive pieces -> four distinct bank groups)
+      const uint4 *xg = reinterpret_cast<const uint4 *>(a.x);
+      const int units = x_pieces_padded * 4, valid = a.K >> 3;
+      for (int p0 = tid; p0 < units; p0 += 4 * CT) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int p = p0 + u * CT;
+          v[u] = p < valid ? ld_x_u4(xg + p) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int p = p0 + u * CT;
+          if (p < units) *reinterpret_cast<uint4 *>(s_x + (p >> 2) * kTmXPitch + (p & 3) * 16) = v[u];
+        }
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
+
+    const uint32_t lane4 = (uint32_t)(lane * 4);
+    const int gsel = g - (t >> 1);                   // sequence j feeds x from the lanes with g == 2j + (t >> 1)
+    const uint32_t x_s = smem_base + (uint32_t)(kTmRing + nsmem * kTmStage) + (uint32_t)(t * kTmXPitch);
+    const float offset = a.offset;
+    const uint32_t taddr_q = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int bs2 = a.bs2_shift;
+    // this lane's four partial sums: rows g, g+8 x slot blocks 2t, 2t+1 = row blocks 4 * (hc0 + q + 4 * (t >> 1)) + 2 * (t & 1) (+1)
+    const int hsel = q + 4 * (t >> 1), bsel = 2 * (t & 1);
+
+    float acc0 = 0.f, acc1 = 0.f;
+    uint32_t b[4];
+    int tl = 0, si = grp;
+    while (si >= spt) { si -= spt; tl++; }
+    for (int n = grp; n < nstages; n += G) {
+      int ntl_ = tl, nsi = si + G;
+      while (nsi >= spt) { nsi -= spt; ntl_++; }
+      const int hc0 = si * 8;
+      // absmax of the four partial sums (clamped inside the row for zero-filled half-chunks: they multiply exact zeros)
+      const int rb = min((hc0 + hsel) * 4 + bsel, kb - 2);
+      float am00, am01, am10, am11;
+      {
+        const int row0 = (t_begin + tl) * 16 + g;
+        const size_t i0 = (size_t)row0 * kb + rb, i1 = i0 + (size_t)8 * kb;
+        if (NESTED) {
+          const uint32_t q0 = *reinterpret_cast<const unsigned short *>(s_abs + (size_t)(tl * 16 + g) * kb + rb);
+          const uint32_t q1 = *reinterpret_cast<const unsigned short *>(s_abs + (size_t)(tl * 16 + g + 8) * kb + rb);
+          const float m0 = __ldg(a.absmax2 + (i0 >> bs2)), m1 = __ldg(a.absmax2 + (i1 >> bs2));
+          am00 = __fadd_rn(__fmul_rn(s_code2[q0 & 0xFFu], m0), offset);
+          am01 = __fadd_rn(__fmul_rn(s_code2[q0 >> 8], m0), offset);
+          am10 = __fadd_rn(__fmul_rn(s_code2[q1 & 0xFFu], m1), offset);
+          am11 = __fadd_rn(__fmul_rn(s_code2[q1 >> 8], m1), offset);
+        } else {
+          const float2 f0 = __ldg(reinterpret_cast<const float2 *>(a.absmax + i0)), f1 = __ldg(reinterpret_cast<const float2 *>(a.absmax + i1));
+          am00 = f0.x; am01 = f0.y; am10 = f1.x; am11 = f1.y;
+        }
+      }
+      const int sl = n % kTmSlots;
+      tc::mbar_wait(tfull + sl * 8, (uint32_t)(n / kTmSlots) & 1u);
+      tc::fence_after_sync();
+      uint32_t v[32];
+      tc::tmem_ld_32x32b_x32(taddr_q + sl * 32, v);
+      tc::tmem_ld_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tempty + sl * 8);
+
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int jh = 0; jh < 2; jh++) {
+        const int hc = hc0 + q + 4 * jh;
+        if (hc < nhc) {                            // warp-uniform: zero-filled half-chunks are skipped
+#pragma unroll
+          for (int jl = 0; jl < 2; jl++) {
+            const int j = 2 * jh + jl;
+            const uint32_t act = (gsel == 2 * j) ? 1u : 0u;
+            const uint32_t xj = x_s + (uint32_t)((hc * 8 + 4 * jl) * kTmXPitch);
+            b[0] = b[1] = b[2] = b[3] = 0u;
+#pragma unroll
+            for (int wd = 0; wd < 4; wd++) {
+              lds_x4_pred(b, xj + wd * 16, act);
+              const uint32_t s0 = v[4 * j + wd], s1 = v[16 + 4 * j + wd];
+#pragma unroll
+              for (int mm = 0; mm < 2; mm++) {
+                const uint32_t selA = 0x7604u | ((2 * mm) << 4), selB = 0x7604u | ((2 * mm + 1) << 4);
+                uint32_t af[4];
+                af[0] = *reinterpret_cast<const uint32_t *>(smem + __byte_perm(s0, lane4, selA));
+                af[1] = *reinterpret_cast<const uint32_t *>(smem + __byte_perm(s1, lane4, selA));
+                af[2] = *reinterpret_cast<const uint32_t *>(smem + __byte_perm(s0, lane4, selB));
+                af[3] = *reinterpret_cast<const uint32_t *>(smem + __byte_perm(s1, lane4, selB));
+                MmaT<T>::mma(d, af, b[2 * mm], b[2 * mm + 1]);
+              }
+            }
+          }
+        }
+      }
+      acc0 = __fmaf_rn(d[0], am00, acc0);
+      acc0 = __fmaf_rn(d[1], am01, acc0);
+      acc1 = __fmaf_rn(d[2], am10, acc1);
+      acc1 = __fmaf_rn(d[3], am11, acc1);
+      if (ntl_ != tl || n + G >= nstages) {   // this warp is done with the tile: park its partial sums
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+        if (t == 0) {
+          float *slot = s_part + (tl * CW + warp) * 16;
+          slot[g] = acc0;
+          slot[g + 8] = acc1;
+        }
+        acc0 = acc1 = 0.f;
+      }
+      tl = ntl_; si = nsi;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
+    for (int i = tid; i < ntl * 16; i += CT) {
+      const int tile_l = i >> 4, row = i & 15;
+      const float *p = s_part + tile_l * CW * 16 + row;
+      float sum = 0.f;
+#pragma unroll
+      for (int wq = 0; wq < CW; wq++) sum += p[wq * 16];
+      const int r = (t_begin + tile_l) * 16 + row;
+      if (r < a.N) reinterpret_cast<T *>(a.out)[r] = from_float<T>(sum);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == CW + 1) tc::tmem_dealloc(tmem_base, 512);
+}
+
 // host: last probe of the block-column kernel -> {cycles, ns}
 void gemv_probe(unsigned long long *out2) {
   cudaMemcpyFromSymbol(out2, g_gemv_probe, sizeof(unsigned long long) * 2);
@@ -1094,6 +1363,45 @@ static void launch_mma_inst(const GemvArgs &a) {
       return;
     }
   }
+  static int impl_tm = -1;
+  if (impl_tm < 0) { const char *e = getenv("BNB_B200_GEMV_IMPL"); impl_tm = (e && e[0] == 'm') ? 1 : 0; }
+  if (VEC4 && impl_tm && a.batch == 1 && a.npeers == 0 && (a.N % 16) == 0 && (reinterpret_cast<uintptr_t>(a.B) % 16 == 0) &&
+      (!NESTED || reinterpret_cast<uintptr_t>(a.qabsmax) % 16 == 0)) {
+    static int cw_env = -1;
+    if (cw_env < 0) { const char *e = getenv("BNB_B200_GEMV_TMW"); cw_env = e ? atoi(e) : 16; }
+    const int cw = cw_env == 12 ? 12 : 16;
+    const int tiles = a.N / 16;
+    const int grid = tiles < num_sms[dev] ? tiles : num_sms[dev];
+    const int nhc = a.K / 256, spt = ceil_div(nhc, 8), kb = a.K / 64;
+    const int xpieces = spt * 64;
+    const int ntl_max = ceil_div(tiles, grid);
+    const int abs_bytes = NESTED ? ((ntl_max * 16 * kb + 15) & ~15) : 0;
+    const size_t fixed = 1024 + kTmRing + (size_t)xpieces * kTmXPitch + abs_bytes + (size_t)ntl_max * cw * 16 * sizeof(float);
+    int nsmem = fixed < (size_t)kBcSmemMax ? (int)(((size_t)kBcSmemMax - fixed) / kTmStage) : 0;
+    { static int cap = -1; if (cap < 0) { const char *e = getenv("BNB_B200_GEMV_SLOTS"); cap = e ? atoi(e) : 6; } if (cap > 0 && nsmem > cap) nsmem = cap; }
+    if (nsmem > kTmMaxStages) nsmem = kTmMaxStages;
+    CUtensorMap tmap;
+    if (nsmem >= 2 && make_tmap_gemv_tm(&tmap, a.B, a.N, a.K)) {
+      const size_t need = fixed + (size_t)nsmem * kTmStage;
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3(grid); lc.blockDim = dim3((cw + 2) * 32); lc.dynamicSmemBytes = need; lc.stream = current_stream();
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      lc.attrs = attr; lc.numAttrs = pdl_off ? 0 : 1;
+#define TM_LAUNCH(CW_)                                                                                                   \
+  do {                                                                                                                  \
+    auto kfn = k_gemv4_tm<T, NESTED, CW_>;                                                                              \
+    latch_error(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kBcSmemMax), "gemv tm smem attr"); \
+    latch_error(cudaLaunchKernelEx(&lc, kfn, a2, tmap, xpieces, tiles, nsmem, abs_bytes), "gemv_4bit (TMEM-staged) launch"); \
+  } while (0)
+      if (cw == 12) TM_LAUNCH(12);
+      else TM_LAUNCH(16);
+#undef TM_LAUNCH
+      check_launch("gemv_4bit (TMEM-staged)");
+      return;
+    }
+  }
   if (VEC4 && impl_bc && a.batch == 1) {
     // block-column kernel, register ring.  Default: 8-warp CTAs, two per SM (<= 113 KB of shared memory and <= 128
     // registers each), so consecutive GEMVs of a stream overlap through programmatic dependent launch; 16-warp
@@ -1107,6 +1415,9 @@ static void launch_mma_inst(const GemvArgs &a) {
     };
     int warps = cfg ? (cfg % 10) * 4 : 8;
     int per_sm = warps <= 8 ? 2 : 1;
+    static int grid_per_sm = -1;   // experiment knob: BNB_B200_GEMV_PERSM=1 -> one 8-warp CTA per SM per kernel, so the NEXT kernel's CTA is co-resident
+    if (grid_per_sm < 0) { const char *e = getenv("BNB_B200_GEMV_PERSM"); grid_per_sm = e ? atoi(e) : 0; }
+    if (grid_per_sm > 0 && grid_per_sm < per_sm) per_sm = grid_per_sm;
     int grid = tiles < num_sms[dev] * per_sm ? tiles : num_sms[dev] * per_sm;
     if (!cfg && smem_need(warps, grid) > (size_t)(113 * 1024)) {
       warps = 16; per_sm = 1;

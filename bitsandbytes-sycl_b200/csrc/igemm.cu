@@ -61,6 +61,22 @@ bool make_tmap_2d(CUtensorMap *map, const void *base, int elem_bytes, uint64_t r
   return true;
 }
 
+// packed 4-bit weight [N, K/2] seen as {128 B inside a half-chunk, 16 rows of a tile, K/256 half-chunks, N/16 tiles};
+// box {64 B, 8 rows, 4 half-chunks, 1 tile} lands in shared memory as [half-chunk][row][64 B], no swizzle (gemv_4bit.cu)
+bool make_tmap_gemv_tm(CUtensorMap *map, const void *base, int N, int K) {
+  auto fn = get_encode_fn();
+  if (!fn) { latch_error(cudaErrorNotSupported, "cuTensorMapEncodeTiled unavailable"); return false; }
+  const uint64_t row_bytes = (uint64_t)K / 2;
+  cuuint64_t dims[4] = {128, 16, (uint64_t)K / 256, (uint64_t)N / 16};
+  cuuint64_t strides[3] = {row_bytes, 128, row_bytes * 16};
+  cuuint32_t box[4] = {64, 8, 4, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { latch_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (gemv) failed"); return false; }
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // tcgen05 kernel
 // ------------------------------------------------------------------------------------------------

@@ -54,6 +54,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
                ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap *m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 // ---- TMEM --------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
@@ -75,6 +80,11 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
+}
+// shared memory -> TMEM, 128 lanes x 256 bits: row i of the K-major operand tile described by `sdesc` (32 bytes of it)
+// lands in lane i, 8 consecutive 32-bit columns starting at taddr.  Asynchronous; completion through tcgen05.commit.
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -116,5 +126,8 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 // 128-byte swizzle).  Returns false (and latches an error) on failure.
 bool make_tmap_2d(CUtensorMap *map, const void *base, int elem_bytes, uint64_t rows, uint64_t cols, uint32_t box_rows,
                   uint32_t box_cols, bool is_bf16_or_f16, bool is_bf16, bool swizzle128 = true);
+
+// host: tensor map of the TMEM-staged GEMV (gemv_4bit.cu k_gemv4_tm; defined in igemm.cu)
+bool make_tmap_gemv_tm(CUtensorMap *map, const void *base, int N, int K);
 
 }  // namespace bnb
