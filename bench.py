@@ -355,10 +355,15 @@ def main():
             if peers is not None:
                 fused_linear(i, x_dev[:, ko:ko + K], q, st)
             else:
-                y = bnb_b200.matmul_4bit(x_dev[:, ko:ko + K], q.t(), quant_state=st)
-                if world > 1:
-                    y = all_gather_features(y, world)
-                y_dev[:, no:no + N] = y.reshape(B, N)
+                if world == 1 and B == 1:
+                    # `out=` is part of the reference signature (matmul_4bit(A, B, quant_state, out, bias)): the GEMV
+                    # writes straight into its slice of the step's output buffer
+                    bnb_b200.matmul_4bit(x_dev[:, ko:ko + K], q.t(), quant_state=st, out=y_dev[:, no:no + N])
+                else:
+                    y = bnb_b200.matmul_4bit(x_dev[:, ko:ko + K], q.t(), quant_state=st)
+                    if world > 1:
+                        y = all_gather_features(y, world)
+                    y_dev[:, no:no + N] = y.reshape(B, N)
             ko += K
             no += N
         if kernel_sync:

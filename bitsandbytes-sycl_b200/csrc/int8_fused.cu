@@ -3,6 +3,8 @@
 // with no host synchronisation -- the reference needs one (nnz, functional.py:2546) plus torch.unique / sort and a
 // dozen indexing kernels to find the outlier columns:
 //
+//   (K <= 4096: k_i8_row_onepass does the statistics AND the quantisation in one pass with the row in registers,
+//    k_i8_fix_outliers then zeroes the outlier columns; larger K uses the two passes below)
 //   k_i8_rowstats_flags   one pass over A: row absmax with |x| >= thr excluded (kgetColRowStats semantics,
 //                         kernel_quant.cpp:3292-3301) + a flag per column that holds any outlier
 //   k_i8_compact          flags -> ascending outlier column list idx[], position map pos[], count (device side)
@@ -102,6 +104,65 @@ __global__ void __launch_bounds__(256) k_i8_quant_rows(const __half *__restrict_
   }
 }
 
+// K <= NV * 256: the whole row lives in registers (NV 128-bit loads in flight per lane), so statistics and quantisation
+// are ONE pass over A.  Outlier COLUMNS are not known yet (they depend on every row): CA is written for all columns and
+// k_i8_fix_outliers zeroes the (few) outlier columns afterwards.
+template <int NV>
+__global__ void __launch_bounds__(256) k_i8_row_onepass(const __half *__restrict__ A, float *__restrict__ rowStats,
+                                                        unsigned char *__restrict__ colflag, signed char *__restrict__ CA,
+                                                        float thr, int rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const __half *row = A + (size_t)r * cols;
+  uint4 raw[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    const int c0 = (i * 32 + lane) * 8;
+    raw[i] = c0 < cols ? ld_stream_u4(row + c0) : make_uint4(0, 0, 0, 0);
+  }
+  float rmax = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    const int c0 = (i * 32 + lane) * 8;
+    const __half *p = reinterpret_cast<const __half *>(&raw[i]);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      float v = fabsf(__half2float(p[j]));
+      if (v >= thr) { colflag[c0 + j] = 1; v = 0.f; }
+      rmax = fmaxf(rmax, v);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+  if (lane == 0) rowStats[r] = rmax;
+  const float scale = __fdiv_rn(127.0f, rmax);
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    const int c0 = (i * 32 + lane) * 8;
+    if (c0 >= cols) continue;
+    const __half *p = reinterpret_cast<const __half *>(&raw[i]);
+    uint32_t q[2] = {0, 0};
+#pragma unroll
+    for (int j = 0; j < 8; j++) q[j >> 2] |= (uint32_t)(quant_s8_(__half2float(p[j]), scale) & 0xFF) << (8 * (j & 3));
+    *reinterpret_cast<uint2 *>(CA + (size_t)r * cols + c0) = make_uint2(q[0], q[1]);
+  }
+}
+
+// zero the outlier columns of CA (_functions.py:382) and gather them into subA (first 16 columns)
+__global__ void __launch_bounds__(256) k_i8_fix_outliers(const __half *__restrict__ A, signed char *__restrict__ CA,
+                                                         __half *__restrict__ subA, const int *__restrict__ idx,
+                                                         const int *__restrict__ count, int rows, int cols, int idx_cap) {
+  const int n = min(*count, idx_cap);
+  if (n <= 0) return;
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < (long)rows * n; i += (long)gridDim.x * 256) {
+    const int r = (int)(i / n), o = (int)(i % n);
+    const int c = idx[o];
+    CA[(size_t)r * cols + c] = 0;
+    if (o < kMaxOutliers) subA[(size_t)r * kMaxOutliers + o] = A[(size_t)r * cols + c];
+  }
+}
+
 __global__ void __launch_bounds__(256) k_i8_subB(const signed char *__restrict__ CB, const float *__restrict__ SCB,
                                                  const int *__restrict__ idx, const int *__restrict__ count,
                                                  __half *__restrict__ subB, int n, int k) {
@@ -150,9 +211,18 @@ int int8_linear_fused(const __half *A, const signed char *CB, const float *SCB, 
   cudaStream_t st = current_stream();
   latch_error(cudaMemsetAsync(colflag, 0, (size_t)k, st), "int8 fused memset");
   latch_error(cudaMemsetAsync(subA, 0, (size_t)m * kMaxOutliers * sizeof(__half), st), "int8 fused memset");
-  k_i8_rowstats_flags<<<ceil_div(m, 8), 256, 0, st>>>(A, SCA, colflag, thr, m, k);
-  k_i8_compact<<<1, 1024, 0, st>>>(colflag, idx, pos, count, k, idx_cap);
-  k_i8_quant_rows<<<ceil_div(m, 8), 256, 0, st>>>(A, SCA, pos, CA, subA, m, k);
+  if (k <= 4096) {
+    // one pass over A: the row stays in registers between the statistics and the quantisation
+    if (k <= 1024) k_i8_row_onepass<4><<<ceil_div(m, 8), 256, 0, st>>>(A, SCA, colflag, CA, thr, m, k);
+    else if (k <= 2048) k_i8_row_onepass<8><<<ceil_div(m, 8), 256, 0, st>>>(A, SCA, colflag, CA, thr, m, k);
+    else k_i8_row_onepass<16><<<ceil_div(m, 8), 256, 0, st>>>(A, SCA, colflag, CA, thr, m, k);
+    k_i8_compact<<<1, 1024, 0, st>>>(colflag, idx, pos, count, k, idx_cap);
+    k_i8_fix_outliers<<<kNumSMs, 256, 0, st>>>(A, CA, subA, idx, count, m, k, idx_cap);
+  } else {
+    k_i8_rowstats_flags<<<ceil_div(m, 8), 256, 0, st>>>(A, SCA, colflag, thr, m, k);
+    k_i8_compact<<<1, 1024, 0, st>>>(colflag, idx, pos, count, k, idx_cap);
+    k_i8_quant_rows<<<ceil_div(m, 8), 256, 0, st>>>(A, SCA, pos, CA, subA, m, k);
+  }
   k_i8_subB<<<(unsigned)ceil_div_ll((long)n * kMaxOutliers, 256), 256, 0, st>>>(CB, SCB, idx, count, subB, n, k);
   check_launch("int8 fused quantisation");
   const int rc = igemm_rowmajor_dequant_outliers_fp16(m, n, k, CA, CB, SCA, SCB, bias, out, subA, subB, count);

@@ -23,81 +23,108 @@ __device__ __forceinline__ void atomic_max_nonneg(float *addr, float v) {
 // ------------------------------------------------------------------------------------------------
 // K5a: row/col absmax (+ per (tile,row) outlier counts when thr > 0)
 // ------------------------------------------------------------------------------------------------
-template <bool VEC>
-__global__ void __launch_bounds__(256) k_col_row_stats(const __half *__restrict__ A, float *rowStats, float *colStats,
-                                                       int *nnz_count_row, float thr, int rows, int cols,
-                                                       int col_tiles, int nbands) {
-  const int lane = threadIdx.x & 31;
-  const long wid = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (wid >= (long)nbands * col_tiles) return;
-  const int band = (int)(wid / col_tiles), ct = (int)(wid % col_tiles);
-  const int c0 = ct * 256 + lane * 8;
-  const int r0 = band * kBandRows;
-  const bool sparse = thr > 0.0f;
+// butterfly reduce-scatter of 8 per-lane values: afterwards v[0] of lane l is the warp-wide reduction of everybody's
+// v[l & 7] (9 shuffles for 8 rows instead of 5 per row)
+template <typename V, typename Op>
+__device__ __forceinline__ void warp_reduce_scatter8(V (&v)[8], int lane, Op op) {
+#pragma unroll
+  for (int o = 4; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; i++) {
+      const V send = up ? v[i] : v[i + o];
+      const V keep = up ? v[i + o] : v[i];
+      v[i] = op(keep, __shfl_xor_sync(0xffffffffu, send, o));
+    }
+  }
+  v[0] = op(v[0], __shfl_xor_sync(0xffffffffu, v[0], 8));
+  v[0] = op(v[0], __shfl_xor_sync(0xffffffffu, v[0], 16));
+}
 
+constexpr int kStatWarpRows = 16;   // rows per warp: one of the reference's 16-row nnz tiles, all 16 loads in flight at once
+constexpr int kStatCtaRows = 8 * kStatWarpRows;
+
+// CTA = 8 warps stacked on ONE 256-column segment (128 rows): column maxima meet in shared memory first, so the global
+// atomics are 256 per CTA; row maxima: one atomic per (row, segment), issued by 8 lanes at a time.
+template <bool VEC, bool SPARSE>
+__global__ void __launch_bounds__(256) k_col_row_stats(const __half *__restrict__ A, float *rowStats, float *colStats,
+                                                       int *nnz_count_row, float thr, int rows, int cols, int col_tiles) {
+  __shared__ int s_cmax[256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ct = blockIdx.x % col_tiles, rband = blockIdx.x / col_tiles;
+  const int c0 = ct * 256 + lane * 8;
+  const int r0 = rband * kStatCtaRows + warp * kStatWarpRows;
+  const int rows16 = ((rows + 15) / 16) * 16;
+  s_cmax[threadIdx.x] = 0;
+  __syncthreads();
+
+  uint4 raw[kStatWarpRows];
+#pragma unroll
+  for (int u = 0; u < kStatWarpRows; u++) {
+    const int r = r0 + u;
+    raw[u] = make_uint4(0, 0, 0, 0);
+    if (r < rows) {
+      if (VEC) {
+        if (c0 < cols) raw[u] = ld_stream_u4(A + (long)r * cols + c0);
+      } else {
+        __half *p = reinterpret_cast<__half *>(&raw[u]);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          if (c0 + j < cols) p[j] = A[(long)r * cols + c0 + j];
+      }
+    }
+  }
   float cmax[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) cmax[j] = 0.0f;  // |x| >= 0, and padded / outlier entries count as 0
-
-  for (int rb = 0; rb < kBandRows; rb += 8) {
-    uint4 raw[8];
+#pragma unroll
+  for (int h = 0; h < kStatWarpRows / 8; h++) {
+    float rm[8];
+    int cn[8];
 #pragma unroll
     for (int u = 0; u < 8; u++) {
-      const int r = r0 + rb + u;
-      raw[u] = make_uint4(0, 0, 0, 0);
-      if (r < rows) {
-        if (VEC) {
-          if (c0 < cols) raw[u] = ld_stream_u4(A + (long)r * cols + c0);
-        } else {
-          __half *p = reinterpret_cast<__half *>(&raw[u]);
-#pragma unroll
-          for (int j = 0; j < 8; j++)
-            if (c0 + j < cols) p[j] = A[(long)r * cols + c0 + j];
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const int r = r0 + rb + u;
-      const __half *p = reinterpret_cast<const __half *>(&raw[u]);
+      const __half *p = reinterpret_cast<const __half *>(&raw[h * 8 + u]);
       float rmax = 0.0f;
       int cnt = 0;
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         float v = fabsf(__half2float(p[j]));
-        if (sparse && v >= thr) { cnt++; v = 0.0f; }
+        if (SPARSE && v >= thr) { cnt++; v = 0.0f; }
         cmax[j] = fmaxf(cmax[j], v);
         rmax = fmaxf(rmax, v);
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
-      if (sparse) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      }
-      if (lane == 0) {
-        if (r < rows) atomic_max_nonneg(rowStats + r, rmax);
-        // tile id = (r/16)*col_tiles + ct; slot +1 (slot 0 stays 0 for the caller's cumsum)
-        if (sparse && nnz_count_row && r < ((rows + 15) / 16) * 16)
-          nnz_count_row[((long)(r / 16) * col_tiles + ct) * 16 + (r % 16) + 1] = (r < rows) ? cnt : 0;
-      }
+      rm[u] = rmax;
+      cn[u] = cnt;
+    }
+    warp_reduce_scatter8(rm, lane, [](float a, float b) { return fmaxf(a, b); });
+    const int r = r0 + h * 8 + (lane & 7);
+    if (lane < 8 && r < rows) atomicMax(reinterpret_cast<int *>(rowStats + r), __float_as_int(rm[0]));   // values >= +0: int order == float order
+    if (SPARSE) {
+      warp_reduce_scatter8(cn, lane, [](int a, int b) { return a + b; });
+      // tile id = (r/16)*col_tiles + ct; slot +1 (slot 0 stays 0 for the caller's cumsum)
+      if (lane < 8 && nnz_count_row && r < rows16)
+        nnz_count_row[((long)(r / 16) * col_tiles + ct) * 16 + (r % 16) + 1] = (r < rows) ? cn[0] : 0;
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; j++)
-    if (c0 + j < cols) atomic_max_nonneg(colStats + c0 + j, cmax[j]);
+  for (int j = 0; j < 8; j++) atomicMax(&s_cmax[lane * 8 + j], __float_as_int(cmax[j]));
+  __syncthreads();
+  const int c = ct * 256 + threadIdx.x;
+  if (c < cols) atomicMax(reinterpret_cast<int *>(colStats + c), s_cmax[threadIdx.x]);
 }
 
 void get_col_row_stats(const __half *A, float *rowStats, float *colStats, int *nnz_count_row, float thr, int rows,
                        int cols) {
   if (rows <= 0 || cols <= 0) return;
   const int col_tiles = ceil_div(cols, 256);
-  const int nbands = ceil_div(rows, kBandRows);
-  const long nwarps = (long)nbands * col_tiles;
-  const unsigned grid = (unsigned)ceil_div_ll(nwarps, 8);
+  const int rbands = ceil_div(ceil_div(rows, 16) * 16, kStatCtaRows);
+  const unsigned grid = (unsigned)((long)rbands * col_tiles);
   const bool vec = (cols % 8 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0);
-  if (vec) k_col_row_stats<true><<<grid, 256, 0, current_stream()>>>(A, rowStats, colStats, nnz_count_row, thr, rows, cols, col_tiles, nbands);
-  else k_col_row_stats<false><<<grid, 256, 0, current_stream()>>>(A, rowStats, colStats, nnz_count_row, thr, rows, cols, col_tiles, nbands);
+  cudaStream_t st = current_stream();
+#define STATS_LAUNCH(V_, S_) k_col_row_stats<V_, S_><<<grid, 256, 0, st>>>(A, rowStats, colStats, nnz_count_row, thr, rows, cols, col_tiles)
+  if (thr > 0.0f) { if (vec) STATS_LAUNCH(true, true); else STATS_LAUNCH(false, true); }
+  else { if (vec) STATS_LAUNCH(true, false); else STATS_LAUNCH(false, false); }
+#undef STATS_LAUNCH
   check_launch("get_col_row_stats");
 }
 

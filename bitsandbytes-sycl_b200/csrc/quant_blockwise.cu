@@ -286,7 +286,6 @@ __global__ void __launch_bounds__(256) k_quantize4_bulk(const T *__restrict__ A,
   constexpr int E = 16 / sizeof(T);
   constexpr int U = 4;
   __shared__ __align__(16) QTables s_lut[1];
-  stage_tables<QT>(s_lut, nullptr, nullptr);
 
   const int lane = threadIdx.x & 31;
   const size_t v0 = ((size_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * (U * 32) + lane;
@@ -294,6 +293,7 @@ __global__ void __launch_bounds__(256) k_quantize4_bulk(const T *__restrict__ A,
   uint4 raw[U];
 #pragma unroll
   for (int u = 0; u < U; u++) raw[u] = ld_stream_u4(A + (v0 + u * 32) * E);
+  stage_tables<QT>(s_lut, nullptr, nullptr);   // after the stream loads are in flight: the table fetch + barrier hide under them
 
 #pragma unroll
   for (int u = 0; u < U; u++) {
@@ -381,12 +381,8 @@ __global__ void __launch_bounds__(256) k_dequantize(const float *__restrict__ co
   constexpr int E = 16 / sizeof(T);
   constexpr int U = 8;
   __shared__ float s_tab[QT == General8bit ? 256 : 16];
-  if (QT == General8bit) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = code[i];
-  } else if (threadIdx.x < 16) {
-    s_tab[threadIdx.x] = g_dq4_table[QT == NF4 ? 1 : 0][threadIdx.x];
-  }
-  __syncthreads();
+  float tab_v = 0.f;   // table entry fetched now, published after the stream loads below are in flight
+  if (QT != General8bit && threadIdx.x < 16) tab_v = g_dq4_table[QT == NF4 ? 1 : 0][threadIdx.x];
 
   const long vcta = (long)blockIdx.x * (256 * U);
   uint32_t raw[U][2];
@@ -420,6 +416,12 @@ __global__ void __launch_bounds__(256) k_dequantize(const float *__restrict__ co
       }
     }
   }
+  if (QT == General8bit) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = code[i];
+  } else if (threadIdx.x < 16) {
+    s_tab[threadIdx.x] = tab_v;
+  }
+  __syncthreads();
 #pragma unroll
   for (int u = 0; u < U; u++) {
     const long e0 = (vcta + u * 256 + threadIdx.x) * E;
