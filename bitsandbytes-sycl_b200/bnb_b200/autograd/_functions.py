@@ -177,7 +177,37 @@ class MatMul8bitLt(torch.autograd.Function):
         if ctx.is_empty:
             bias_grad = None if ctx.bias is None else torch.zeros_like(ctx.bias)
             return torch.zeros_like(ctx.A), torch.zeros_like(ctx.B), None, bias_grad, None
-        raise NotImplementedError("MatMul8bitLt.backward is outside this round's scope (SURVEY.md 8f, item 2)")
+        # reference :436-483.  Same quantities, but the two int8 products run on the row-major tcgen05 GEMM
+        # (C[i, j] = sum_k A[i, k] * B[j, k]) instead of col32 / col_turing operands: the operand that the reference
+        # re-lays out with transform(..., transpose=True) is simply transposed here.
+        req_gradA, req_gradB, _, req_gradBias, _ = ctx.needs_input_grad
+        CAt, subA, A = ctx.tensors
+        SCAt, idx = ctx.tensor_states
+        state = ctx.state
+        grad_A = grad_B = grad_bias = None
+        if req_gradBias:
+            grad_bias = grad_output.sum(0, dtype=ctx.dtype_bias)
+        if len(grad_output.shape) == 3:
+            grad_output = grad_output.reshape(-1, grad_output.shape[-1]).contiguous()
+        Cgrad, Cgradt, SCgrad, SCgradt, _ = F.double_quant(grad_output.to(torch.float16))
+        if req_gradB:
+            # grad_B[j, c] = sum_i grad[i, j] * A[i, c], both quantised column-wise (statistics over the token axis)
+            grad_B = F.int8_linear_dequant(Cgradt.t().contiguous(), CAt.t().contiguous(), SCgradt, SCAt)
+            if state.threshold > 0.0 and subA is not None:
+                grad_B[:, idx] += torch.matmul(grad_output.t(), subA)
+        if req_gradA:
+            if state.CBt is not None:
+                # grad_A[i, c] = sum_j grad[i, j] * B[j, c]: grad quantised row-wise, B column-wise
+                if state.CxBt is None:
+                    state.CxBt, state.SBt = state.CBt.t().contiguous(), (tuple(state.CBt.t().shape), "row")
+                grad_A = F.int8_linear_dequant(Cgrad, state.CxBt, SCgrad, state.SCBt).view(ctx.grad_shape).to(ctx.dtype_A)
+            else:
+                CBrow = state.CB if state.CB is not None else (state.CxB if (state.SB and state.SB[1] == "row") else None)
+                if CBrow is None:
+                    raise Exception("State must contain either CBt or CB or CxB matrix for backward")
+                CB = CBrow.to(ctx.dtype_A, copy=True).mul_(state.SCB.unsqueeze(1).mul(1.0 / 127.0))
+                grad_A = torch.matmul(grad_output.to(ctx.dtype_A), CB).view(ctx.grad_shape).to(ctx.dtype_A)
+        return grad_A, grad_B, None, grad_bias, None
 
 
 class MatMul4Bit(torch.autograd.Function):

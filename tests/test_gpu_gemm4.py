@@ -86,3 +86,55 @@ def test_gemm_4bit_refuses_what_it_cannot_do(F):
     import bnb_b200
     y = bnb_b200.matmul_4bit(x, q.t(), quant_state=st)
     assert y.shape == (8, 64) and torch.isfinite(y).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY 8f "next" rows on the 4-bit side: state-dict wire format and the backward caller
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("quant_type", ["nf4", "fp4"])
+def test_linear4bit_state_dict_roundtrip(F, quant_type):
+    """Linear4bit._save_to_state_dict (reference modules.py:436-445) writes the packed weight plus the QuantState
+    components (absmax, nested state, `quant_state.bitsandbytes__<type>` JSON blob); Params4bit.from_prequantized
+    (:281-311) rebuilds the parameter.  The reloaded layer must produce bit-identical outputs."""
+    import bnb_b200
+    torch.manual_seed(11)
+    k, n = 512, 256
+    lin = bnb_b200.nn.Linear4bit(k, n, bias=True, compute_dtype=torch.bfloat16, compress_statistics=True,
+                                 quant_type=quant_type).cuda()
+    x1 = torch.randn(1, k, device="cuda", dtype=torch.bfloat16)
+    x8 = torch.randn(8, k, device="cuda", dtype=torch.bfloat16)
+    with torch.no_grad():
+        y1, y8 = lin(x1), lin(x8)
+    sd = lin.state_dict()
+    qs_keys = [key for key in sd if key.startswith("weight.")]
+    assert any("quant_state.bitsandbytes__" + quant_type in key for key in qs_keys)
+    assert "weight.absmax" in sd and "weight.nested_absmax" in sd and sd["weight"].dtype == torch.uint8
+    stats = {key[len("weight."):]: v for key, v in sd.items() if key.startswith("weight.")}
+    lin2 = bnb_b200.nn.Linear4bit(k, n, bias=True, compute_dtype=torch.bfloat16, compress_statistics=True,
+                                  quant_type=quant_type)
+    lin2.weight = bnb_b200.nn.Params4bit.from_prequantized(sd["weight"], stats, device="cuda")
+    lin2.bias = torch.nn.Parameter(sd["bias"].clone())
+    lin2 = lin2.cuda()
+    with torch.no_grad():
+        z1, z8 = lin2(x1), lin2(x8)
+    assert torch.equal(y1, z1) and torch.equal(y8, z8)
+    assert lin2.weight.quant_state == lin.weight.quant_state
+
+
+def test_matmul4bit_backward(F):
+    """MatMul4Bit.backward (reference _functions.py:520-540): grad_A = grad_out @ dequant(W), grad_bias = sum."""
+    import bnb_b200
+    torch.manual_seed(12)
+    k, n, b = 512, 256, 24
+    W = (torch.randn(n, k, device="cuda") * 0.02).to(torch.bfloat16)
+    q, st = F.quantize_4bit(W, blocksize=64, compress_statistics=True, quant_type="nf4")
+    Wd = F.dequantize_4bit(q, st).float()
+    x = torch.randn(b, k, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    bias = torch.randn(n, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    y = bnb_b200.matmul_4bit(x, q.t(), quant_state=st, bias=bias)
+    g = torch.randn(b, n, device="cuda", dtype=torch.bfloat16)
+    y.backward(g)
+    gA = g.float() @ Wd
+    assert float((x.grad.float() - gA).norm() / gA.norm()) < 5e-3
+    gb = g.float().sum(0)
+    assert float((bias.grad.float() - gb).norm() / gb.norm()) < 1e-2

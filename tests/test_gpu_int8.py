@@ -289,3 +289,68 @@ def test_int8_linear_fused_exact_vs_oracle(F):
     acc = orc.igemm_rowmajor(CA.cpu().numpy(), CB.cpu().numpy())
     ref = orc.mm_dequant(acc, SCA.cpu().numpy(), SCB.cpu().numpy(), m, n, bias.view(torch.int16).numpy().view(np.uint16), col32=False)
     assert np.array_equal(y.cpu().view(torch.int16).numpy().view(np.uint16), ref.view(np.uint16))
+
+
+# ------------------------------------------------------------------------------------------------
+# MatMul8bitLt.backward (reference autograd/_functions.py:436-483) -- SURVEY 8f item 2
+# ------------------------------------------------------------------------------------------------
+def _rel(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm())
+
+
+@pytest.mark.parametrize("has_fp16_weights", [True, False])
+@pytest.mark.parametrize("threshold", [0.0, 6.0])
+def test_matmul8bitlt_backward(F, has_fp16_weights, threshold):
+    """Gradients of Linear8bitLt against the fp32 linear layer with the same weights: int8 quantisation noise only
+    (the reference's own tests use statistical tolerances, tests_pvc/autograd.py:277-280, 389-391)."""
+    import bnb_b200
+    torch.manual_seed(7)
+    m, k, n = 64, 256, 128
+    W = (torch.randn(n, k) * 0.05).half()
+    bias = (torch.randn(n) * 0.1).half()
+    x = torch.randn(m, k).half()
+    if threshold > 0:
+        x[:, 5] = 8.0
+        x[3, 77] = -9.0
+    lin = bnb_b200.nn.Linear8bitLt(k, n, bias=True, has_fp16_weights=has_fp16_weights, threshold=threshold)
+    lin.weight.data.copy_(W)
+    lin.bias.data.copy_(bias)
+    lin = lin.cuda().half()
+    lin.train()
+    xg = x.cuda().clone().requires_grad_(True)
+    y = lin(xg)
+    g = torch.randn(m, n, device="cuda").half()
+    y.backward(g)
+    # fp32 reference
+    xr = x.cuda().float().requires_grad_(True)
+    Wr = W.cuda().float().requires_grad_(True)
+    br = bias.cuda().float().requires_grad_(True)
+    yr = xr @ Wr.t() + br
+    yr.backward(g.float())
+    assert _rel(y, yr) < 0.02
+    assert _rel(xg.grad, xr.grad) < 0.03
+    assert _rel(lin.bias.grad, br.grad) < 0.01
+    if has_fp16_weights:
+        assert lin.weight.grad is not None
+        assert _rel(lin.weight.grad, Wr.grad) < 0.03
+    else:
+        assert lin.weight.grad is None   # frozen int8 weight (LoRA-style fine-tuning): only grad_A flows
+
+
+def test_linear8bitlt_state_dict_roundtrip(F):
+    """SCB + weight_format travel through state_dict and the reloaded module gives identical outputs (reference
+    modules.py:725-796)."""
+    import bnb_b200
+    torch.manual_seed(3)
+    k, n = 256, 128
+    lin = bnb_b200.nn.Linear8bitLt(k, n, bias=True, has_fp16_weights=False, threshold=6.0).cuda().half()
+    x = torch.randn(16, k, device="cuda").half()
+    with torch.no_grad():
+        y0 = lin(x)
+    sd = lin.state_dict()
+    assert "SCB" in sd and "weight_format" in sd and sd["weight"].dtype == torch.int8
+    lin2 = bnb_b200.nn.Linear8bitLt(k, n, bias=True, has_fp16_weights=False, threshold=6.0).cuda().half()
+    lin2.load_state_dict(sd)
+    with torch.no_grad():
+        y1 = lin2(x)
+    assert torch.equal(y0, y1)
