@@ -207,7 +207,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
                     help="N>1: output all-gather fused into the GEMV epilogue (peer stores), or one NCCL all-gather per linear")
-    ap.add_argument("--sync", default="kernel", choices=["kernel", "barrier"],
+    ap.add_argument("--sync", default="barrier", choices=["kernel", "barrier"],
                     help="N>1 fused collective: ordering folded into the GEMV kernels, or one symmetric-memory barrier launch per consumer group")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph of the step")
     args = ap.parse_args()
@@ -235,7 +235,7 @@ def main():
 
     shapes = LAYER_SHAPES_7B if args.workload == "llama2-7b" else LAYER_SHAPES_70B
     if args.workload == "llama3-70b":
-        args.layers = min(args.layers, 2)
+        args.layers = min(args.layers, 8)      # 8 layers = 3.5 GB of NF4+DQ weights: > L2 per GPU even when sharded 8 ways
     dtype = torch.bfloat16
     B = args.batch
 
