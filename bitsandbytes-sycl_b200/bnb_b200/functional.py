@@ -487,8 +487,16 @@ def gemv_4bit(A: Tensor, B: Tensor, out: Optional[Tensor] = None, transposed_A=F
         offset = getattr(state, "_offset_host", None)
         if offset is None:  # one host read per weight, cached: the scalar torch computed at quantize time
             offset = state._offset_host = float(state.offset)
+        tabs = getattr(state, "_tables_host", None)
+        if tabs is None:    # host copies of the two code tables, once per weight (like the offset scalar above)
+            if code.numel() == 16 and s2.code.numel() == 256:
+                tabs = ((ct.c_float * 16)(*code.float().cpu().tolist()), (ct.c_float * 256)(*s2.code.float().cpu().tolist()))
+            else:
+                tabs = (None, None)
+            state._tables_host = tabs
         prev = pre_call(A.device)
         is_on_gpu([B, A, out, state.absmax, s2.absmax, s2.code, code])
+        lib.cbnb_set_gemv_host_tables(tabs[0], tabs[1])
         if peer_outs:
             arr = (ct.c_void_p * len(peer_outs))(*[ct.c_void_p(int(p)) for p in peer_outs])
             getattr(lib, f"cgemm_4bit_inference_nested_push_{_SUFFIX[A.dtype]}")(

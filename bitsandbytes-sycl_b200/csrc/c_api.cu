@@ -28,6 +28,7 @@ template <typename T, int QT> void quantize_blockwise(const float *, const T *, 
 template <typename T, int QT> void dequantize_blockwise(const float *, const unsigned char *, const float *, T *, int, long);
 long long selftest_quant_lut(int qtype);
 void gemv_probe(unsigned long long *out2);
+void set_gemv_host_tables(const float *code16, const float *code2_256);
 template <typename T> void gemv_4bit(int, int, int, const T *, const unsigned char *, const float *, const float *, T *, int, int, int, int);
 struct GemvSync;
 void epoch_bump(unsigned int *epoch);
@@ -63,6 +64,7 @@ const char *cbnb_last_error_string(void) { return tl_error_msg; }
 const char *cbnb_version(void) { return "bnb_b200 sm_100a r1"; }
 long long cbnb_selftest_quant_lut(int qtype) { return selftest_quant_lut(qtype); }
 void cbnb_debug_gemv_probe(unsigned long long *cycles_ns) { gemv_probe(cycles_ns); }
+void cbnb_set_gemv_host_tables(const float *code16_host, const float *code2_256_host) { set_gemv_host_tables(code16_host, code2_256_host); }
 
 // ---------------------------------------------------------------- blockwise quantize (pythonInterface.cpp:203-217)
 #define QUANT_FN(name, T, QT) \

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <type_traits>
 
+#include "codebooks.cuh"
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -66,6 +67,11 @@ struct GemvArgs {
   const float *code2;        // fp32[256]                       (nested)
   float offset;
   const float *code;         // fp32[16]
+  // 2: the host verified (cbnb_set_gemv_host_tables) that code == the NF4 table -> the kernel builds its lookup table
+  // from immediates.  A small global load issued at kernel start queues behind the weight stream of the CTAs already
+  // running on the SM and takes 0.6-2.5 us to come back -- on the critical path of every launch.  (Passing the
+  // tables by value was measured too: kernel parameters come through the same memory system, no gain.)
+  int tables_in_args;
   void *out;                 // [batch, N] T
   // multi-GPU (N-sharded linear): the same output slice is also stored into the peers' copies of the full
   // output vector through NVLink peer mappings -- the all-gather happens in the GEMV epilogue
@@ -514,7 +520,7 @@ void epoch_bump(unsigned int *epoch) {
 }
 
 // debug probe (flags bit 1): SM cycles and nanoseconds spent by CTA 0 -> effective SM clock under this kernel's load
-__device__ unsigned long long g_gemv_probe[2];
+__device__ unsigned long long g_gemv_probe[12];   // [0] cycles, [1] ns of the probed CTA; [2..6] phase timestamps (ns since entry)
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long v;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
@@ -537,13 +543,44 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
+  // table constants first: ONE round of small global loads (the 16 code values as four 128-bit loads, this thread's
+  // low-nibble value, its code2 entries), issued AHEAD of the weight stream so that they are not queued behind it.
+  // (A load per LUT entry behind the weight prefetch cost eight serial round trips, ~2 us of every launch on the
+  // critical path -- measured with the phase probe.)
+  constexpr int CT0 = WARPS * 32;
+  float c2v[(256 + CT0 - 1) / CT0];
+  float cv[16];
+  float clo;
+  if (a.tables_in_args == 2) {     // the host verified code == the NF4 table: immediates, no memory access at all
+    constexpr float nf4[16] = BNB_NF4_TABLE;
+#pragma unroll
+    for (int u = 0; u < (256 + CT0 - 1) / CT0; u++) c2v[u] = (NESTED && tid + u * CT0 < 256) ? __ldg(a.code2 + tid + u * CT0) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 16; u++) cv[u] = nf4[u];
+    clo = nf4[0];
+#pragma unroll
+    for (int u = 1; u < 16; u++) clo = (((tid >> 3) & 15) == u) ? nf4[u] : clo;
+  } else {
+#pragma unroll
+    for (int u = 0; u < (256 + CT0 - 1) / CT0; u++) c2v[u] = (NESTED && tid + u * CT0 < 256) ? __ldg(a.code2 + tid + u * CT0) : 0.f;
+    if ((reinterpret_cast<uintptr_t>(a.code) & 15) == 0) {
+      const float4 *cg = reinterpret_cast<const float4 *>(a.code);
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const float4 f = __ldg(cg + u); cv[4 * u] = f.x; cv[4 * u + 1] = f.y; cv[4 * u + 2] = f.z; cv[4 * u + 3] = f.w; }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 16; u++) cv[u] = __ldg(a.code + u);
+    }
+    clo = __ldg(a.code + ((tid >> 3) & 15));
+  }
   unsigned long long probe_c = 0, probe_t = 0;
-  if ((a.flags & 2) && blockIdx.x == 0 && tid == 0) { probe_c = clock64(); probe_t = globaltimer_ns(); }
+  const bool probing = (a.flags & 2) && blockIdx.x == gridDim.x / 2 && tid == 0;
+  if (probing) { probe_c = clock64(); probe_t = globaltimer_ns(); }
   const int kb = a.K >> 6;                 // blocks per row
   const int nch = (a.K + 511) >> 9;        // 512-element chunks per row (the last one may be half)
   const int row_bytes = a.K >> 1;
-  const int t_begin = (int)((long)blockIdx.x * tiles_total / gridDim.x);
-  const int t_end = (int)((long)(blockIdx.x + 1) * tiles_total / gridDim.x);
+  const int t_begin = (int)(blockIdx.x * (unsigned)tiles_total / gridDim.x);          // < 2^32: grid <= 2 * 148, tiles < 2^22
+  const int t_end = (int)((blockIdx.x + 1) * (unsigned)tiles_total / gridDim.x);
   const int ntl = t_end - t_begin;
 
   uint32_t w[DEPTH][2][2][8];   // [ring slot][block t / t+4][row half][32 bytes = one sector per lane]
@@ -602,16 +639,34 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
   // constants (code, code2), so it may run before the previous kernel of the stream has finished
   {
     constexpr int CT = WARPS * 32;
-    for (int i = tid; i < 256; i += CT) if (NESTED) s_code2[i] = __ldg(a.code2 + i);
+    if (probing) g_gemv_probe[7] = globaltimer_ns() - probe_t;      // first weight loads issued
+    // ONE round of global loads for all tables (the 16 code values as four 128-bit loads + this thread's low-nibble
+    // value + its code2 entries); the LUT is then built from registers.  A load per LUT entry costs eight serial L2
+    // round trips here -- 2 us of every launch, on the critical path (measured with the phase probe).
+#pragma unroll
+
     // byte e -> {T(code[e >> 4]), T(code[e & 15])}, replicated for the 32 lanes (bank == lane): 8 threads write
-    // one 128-byte entry with conflict-free 128-bit stores
+    // one 128-byte entry with conflict-free 128-bit stores.  Thread (tid >> 3) + it * CT/8 handles entries whose low
+    // nibble is fixed ((tid >> 3) & 15) and whose high nibble is a compile-time function of `it` plus bits of tid.
     const int j = tid & 7;
-    for (int e = tid >> 3; e < 256; e += CT / 8) {
-      const uint32_t v = (MmaT<T>::pack(__ldg(a.code + (e >> 4)), 0.0f) & 0xFFFFu) | (MmaT<T>::pack(__ldg(a.code + (e & 15)), 0.0f) << 16);
-      *reinterpret_cast<uint4 *>(smem + e * 256 + j * 16) = make_uint4(v, v, v, v);
+    const uint32_t lo16 = MmaT<T>::pack(clo, 0.0f) << 16;
+    constexpr int EPI = CT / 8;                      // entries per iteration (32 for 8 warps, 64 for 16)
+    const int hsel = (tid >> 3) >> 4;                // 0 .. EPI/16 - 1
+#pragma unroll
+    for (int it = 0; it < (256 + EPI - 1) / EPI; it++) {
+      const int e = (tid >> 3) + it * EPI;
+      constexpr int HB = EPI / 16;
+      float chi = cv[it * HB < 15 ? it * HB : 15];
+#pragma unroll
+      for (int h = 1; h < HB; h++) chi = (hsel == h) ? cv[it * HB + h < 15 ? it * HB + h : 15] : chi;
+      const uint32_t v = (MmaT<T>::pack(chi, 0.0f) & 0xFFFFu) | lo16;
+      if (e < 256) *reinterpret_cast<uint4 *>(smem + e * 256 + j * 16) = make_uint4(v, v, v, v);
     }
+    if (probing) g_gemv_probe[9] = globaltimer_ns() - probe_t;      // LUT stored
     for (int i = tid; i < ntl * WARPS * 16; i += CT) s_part[i] = 0.f;
+    if (probing) g_gemv_probe[2] = globaltimer_ns() - probe_t;      // prologue (tables) done, about to wait
     asm volatile("griddepcontrol.wait;" ::: "memory");     // x (and out) belong to the previous kernel until here
+    if (probing) g_gemv_probe[3] = globaltimer_ns() - probe_t;      // previous kernel complete
     if (a.sig_local != nullptr && a.do_wait) {
       // first kernel of a consumer group on an N-sharded stack: the gathered vectors of the previous group must
       // be complete on this GPU, i.e. every peer has published a sequence number >= ours (bounded spin: trap, never hang)
@@ -641,7 +696,12 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
       }
     }
   }
+  // code2 is first needed by the de-nest at the end of the first item: stored last, its load had the whole prologue
+#pragma unroll
+  for (int u = 0; u < (256 + CT0 - 1) / CT0; u++) if (NESTED && tid + u * CT0 < 256) s_code2[tid + u * CT0] = c2v[u];
+  if (probing) g_gemv_probe[8] = globaltimer_ns() - probe_t;        // code2 arrived and stored
   __syncthreads();
+  if (probing) g_gemv_probe[4] = globaltimer_ns() - probe_t;        // x in shared memory
 
   const uint32_t lane4 = (uint32_t)(lane * 4);
   const uint32_t act0 = (g == t), act1 = (g == t + 4);
@@ -711,7 +771,9 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
       tl = ntl_; c = nc;
     }
   }
+  if (probing) g_gemv_probe[5] = globaltimer_ns() - probe_t;        // warp 0 finished its items
   __syncthreads();
+  if (probing) g_gemv_probe[6] = globaltimer_ns() - probe_t;        // every warp finished
   for (int i = tid; i < ntl * 16; i += (WARPS * 32)) {
     const int tile_l = i >> 4, row = i & 15;
     const float *p = s_part + tile_l * WARPS * 16 + row;
@@ -738,7 +800,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
       }
     }
   }
-  if ((a.flags & 2) && blockIdx.x == 0 && tid == 0) {
+  if (probing) {
     g_gemv_probe[0] = clock64() - probe_c;
     g_gemv_probe[1] = globaltimer_ns() - probe_t;
   }
@@ -1247,7 +1309,7 @@ k_gemv4_tm(const GemvArgs a, const __grid_constant__ CUtensorMap tmapB, int x_pi
 
 // host: last probe of the block-column kernel -> {cycles, ns}
 void gemv_probe(unsigned long long *out2) {
-  cudaMemcpyFromSymbol(out2, g_gemv_probe, sizeof(unsigned long long) * 2);
+  cudaMemcpyFromSymbol(out2, g_gemv_probe, sizeof(unsigned long long) * 12);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1496,6 +1558,10 @@ void gemv_4bit(int m, int n, int k, const T *A, const unsigned char *B, const fl
   check_launch("gemv_4bit (generic)");
 }
 
+// host copies of code[16] / code2[256] for the NEXT nested GEMV of this thread (consumed by that call)
+static thread_local const float *tl_code_host = nullptr, *tl_code2_host = nullptr;
+void set_gemv_host_tables(const float *code16, const float *code2_256) { tl_code_host = code16; tl_code2_host = code2_256; }
+
 template <typename T>
 void gemv_4bit_nested(int m, int n, int k, const T *A, const unsigned char *B, const unsigned char *qabsmax,
                       const float *absmax2, const float *code2, float offset, const float *datatype, T *out,
@@ -1511,6 +1577,13 @@ void gemv_4bit_nested(int m, int n, int k, const T *A, const unsigned char *B, c
   a.N = m; a.K = k; a.batch = n; a.blocksize = blocksize;
   a.x = A; a.B = B; a.qabsmax = qabsmax; a.absmax2 = absmax2; a.code2 = code2; a.offset = offset;
   a.code = datatype; a.out = out;
+  if (tl_code_host != nullptr) {
+    static const float nf4[16] = BNB_NF4_TABLE;
+    bool same = true;
+    for (int i = 0; i < 16; i++) same = same && (tl_code_host[i] == nf4[i]);
+    if (same) a.tables_in_args = 2;
+  }
+  tl_code_host = tl_code2_host = nullptr;
   if (npeers > 0) {
     // peer stores exist only in the block-column kernel (batch 1, blocksize 64, K % 256 == 0, K small enough for shared memory)
     if (npeers > 7 || n != 1 || blocksize != 64 || (k % 256) != 0 || k > 28672 || !peer_outs) {

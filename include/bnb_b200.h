@@ -116,13 +116,20 @@ BNB_B200_API const char *cbnb_version(void);
  * 4-bit quantiser disagrees with the reference decision tree; qtype 1 = FP4, 2 = NF4. Must return 0. */
 BNB_B200_API long long cbnb_selftest_quant_lut(int qtype);
 
-/* debug: {SM cycles, nanoseconds} CTA 0 of the last block-column GEMV spent (recorded only when the
- * environment has BNB_B200_GEMV_PROBE=1) -> effective SM clock under the kernel's own load */
+/* debug: out[12] = {SM cycles, nanoseconds} the middle CTA of the last block-column GEMV spent, then the nanoseconds
+ * since its entry at which it (2) finished its tables, (3) saw the previous kernel complete, (4) had x in shared
+ * memory, (5) finished warp 0's items, (6) finished every warp's items; (7) first weight loads issued, (8) code2 stored, (9) LUT stored; out[10..11] unused.  Recorded only when the
+ * environment has BNB_B200_GEMV_PROBE=1. */
 BNB_B200_API void cbnb_debug_gemv_probe(unsigned long long *cycles_ns);
 
 /* GEMV with the NESTED (double-quantised) absmax consumed directly: qabsmax uint8 [N*K/blocksize],
  * absmax2 fp32 [ceil(nblocks/blocksize2)], code2 fp32[256], offset scalar. De-nesting is
  * fl(fl(code2[q] * absmax2[i / blocksize2]) + offset), identical to functional.py:1982-1984. */
+/* Optional, per thread, consumed by the NEXT cgemm_4bit_inference_nested[_push]_* call: HOST copies of that call's
+ * `datatype` (16 floats) and `code2` (256 floats; may be NULL).  When the host copy equals the NF4 table the kernel
+ * builds its lookup table from immediates instead of waiting for a global load (which queues behind the weight
+ * stream of a busy GPU).  The device pointers must still be passed. */
+BNB_B200_API void cbnb_set_gemv_host_tables(const float *code16_host, const float *code2_256_host);
 BNB_B200_API void cgemm_4bit_inference_nested_fp16(int m, int n, int k, void *A, unsigned char *B, unsigned char *qabsmax, float *absmax2, float *code2, float offset, float *datatype, void *out, int lda, int ldb, int ldc, int blocksize, int blocksize2);
 BNB_B200_API void cgemm_4bit_inference_nested_bf16(int m, int n, int k, void *A, unsigned char *B, unsigned char *qabsmax, float *absmax2, float *code2, float offset, float *datatype, void *out, int lda, int ldb, int ldc, int blocksize, int blocksize2);
 

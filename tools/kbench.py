@@ -116,10 +116,12 @@ def bench_gemv(iters, shapes=None, dtypes=(torch.bfloat16,)):
             extra = {}
             if os.environ.get("BNB_B200_GEMV_PROBE") == "1":
                 import ctypes as ct
-                buf = (ct.c_ulonglong * 2)()
+                buf = (ct.c_ulonglong * 12)()
                 F.lib.cbnb_debug_gemv_probe(buf)
                 if buf[1]:
-                    extra = {"cta0_us": round(buf[1] / 1e3, 2), "sm_mhz_in_kernel": round(buf[0] * 1e3 / buf[1], 1)}
+                    extra = {"cta_us": round(buf[1] / 1e3, 2), "sm_mhz_in_kernel": round(buf[0] * 1e3 / buf[1], 1),
+                             "phase_us": {"loads_issued": buf[7] / 1e3, "code2_in": buf[8] / 1e3, "lut_done": buf[9] / 1e3, "tables": buf[2] / 1e3, "prev_done": buf[3] / 1e3, "x_ready": buf[4] / 1e3,
+                                          "warp0_done": buf[5] / 1e3, "all_done": buf[6] / 1e3}}
             report(f"gemv_nf4_nested_{str(dt).split('.')[-1]}_{N}x{K}", us, gemv_bytes(N, K), buffers=nbuf, **extra)
             del packs, outs
             torch.cuda.empty_cache()
