@@ -167,3 +167,46 @@ def test_gemv_generic_path_odd_shapes(F):
     assert F.lib.cbnb_last_error() == 0
     exact = orc.gemm_4bit_exact(x.numpy(), "fp32", q_ref, am_ref, code, 1, N, K, bs)[0]
     assert rel_l2(out.cpu().numpy(), exact) < 2e-6
+
+
+def test_gemv_host_tables_hint_is_bit_identical(F):
+    """cbnb_set_gemv_host_tables (NF4 lookup table from immediates) must not change a single output bit; a table that
+    is NOT NF4 (FP4) must ignore the hint's fast path and still be exact."""
+    import ctypes as ct
+    for qtype in ("nf4", "fp4"):
+        W, x, q, st = make_case(F, 1024, 4096, "bf16", qtype=qtype, seed=21)
+        y_hint = F.gemv_4bit(x.cuda(), q.t(), state=st)               # the Python mirror passes the host tables
+        assert getattr(st, "_tables_host", None) is not None
+        saved, st._tables_host = st._tables_host, (None, None)
+        y_plain = F.gemv_4bit(x.cuda(), q.t(), state=st)              # device-pointer tables only
+        st._tables_host = saved
+        assert torch.equal(y_hint.view(torch.int16), y_plain.view(torch.int16)), qtype
+
+
+@pytest.mark.parametrize("impl", ["m", "t"])
+def test_experimental_gemv_kernels_stay_parity_green(impl):
+    """The TMEM-staged (BNB_B200_GEMV_IMPL=m) and the first-session MMA (=t) kernels are selectable experiments
+    (DESIGN.md K3); they must keep producing the block-column kernel's accuracy.  Run in a subprocess: the selection
+    is read once per process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, torch, numpy as np\n"
+        f"sys.path[:0] = [{root!r}, {os.path.join(root, 'bitsandbytes-sycl_b200')!r}, {os.path.join(root, 'tests')!r}]\n"
+        "from bnb_b200 import functional as F\n"
+        "torch.manual_seed(5)\n"
+        "for (N, K) in [(4096, 4096), (1024, 11008), (176, 8192)]:\n"
+        "    W = (torch.randn(N, K) * 0.02).bfloat16().cuda()\n"
+        "    x = torch.randn(1, K).bfloat16().cuda()\n"
+        "    q, st = F.quantize_4bit(W, blocksize=64, compress_statistics=True, quant_type='nf4')\n"
+        "    y = F.gemv_4bit(x, q.t(), state=st).double()\n"
+        "    import copy; st32 = copy.copy(st); st32.dtype = torch.float32   # exact weights: code * absmax in fp32\n"
+        "    ref = x.double() @ F.dequantize_4bit(q, st32).double().t()\n"
+        "    err = float((y - ref).norm() / ref.norm())\n"
+        "    assert err < 2.5e-3, (N, K, err)\n"
+        "print('ok')\n")
+    env = dict(os.environ, BNB_B200_GEMV_IMPL=impl)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
