@@ -529,6 +529,59 @@ def gemv_4bit(A: Tensor, B: Tensor, out: Optional[Tensor] = None, transposed_A=F
     return out
 
 
+def gemv_4bit_multi(A: Tensor, Bs, states, outs=None):
+    """ADDITIVE: out_i = A @ dequant(B_i)^T for up to four nested-absmax 4-bit weights that share the activation row A
+    (q/k/v, gate/up of a decoder layer) in ONE launch.  Bit-identical to gemv_4bit per matrix; falls back to the single
+    calls for shapes the native path does not take.  Bs: packed weights as passed to gemv_4bit (already .t()-viewed)."""
+    n = len(Bs)
+    if outs is None:
+        outs = [None] * n
+    s0 = states[0]
+    ok = (1 <= n <= 4 and A.numel() == A.shape[-1] and A.dtype in (torch.float16, torch.bfloat16)
+          and all(st.nested and st.blocksize == 64 and st.shape[1] == s0.shape[1] and st.quant_type == s0.quant_type
+                  and st.state2.blocksize == s0.state2.blocksize for st in states)
+          and s0.shape[1] % 256 == 0 and A.shape[-1] == s0.shape[1])
+    if ok:
+        same = getattr(s0, "_multi_code2_checked", None)
+        if same is None:   # the shared dynamic map: checked once per group (all bitsandbytes states use the same one)
+            same = s0._multi_code2_checked = all(torch.equal(st.state2.code, s0.state2.code) for st in states[1:])
+        ok = same
+    if not ok:
+        return [gemv_4bit(A, B, out=o, state=st) for B, st, o in zip(Bs, states, outs)]
+    _require_cuda(A, "gemv_4bit_multi")
+    A = A.contiguous()
+    k = s0.shape[1]
+    outs = [o if o is not None else torch.empty((*A.shape[:-1], st.shape[0]), dtype=A.dtype, device=A.device)
+            for o, st in zip(outs, states)]
+    code = s0.code.to(A.device)
+    offs = []
+    for st in states:
+        off = getattr(st, "_offset_host", None)
+        if off is None:
+            off = st._offset_host = float(st.offset)
+        offs.append(off)
+    tabs = getattr(s0, "_tables_host", None)
+    if tabs is None:
+        if code.numel() == 16 and s0.state2.code.numel() == 256:
+            tabs = ((ct.c_float * 16)(*code.float().cpu().tolist()), (ct.c_float * 256)(*s0.state2.code.float().cpu().tolist()))
+        else:
+            tabs = (None, None)
+        s0._tables_host = tabs
+    vp = ct.c_void_p
+    prev = pre_call(A.device)
+    is_on_gpu([A, code, s0.state2.code] + list(Bs) + list(outs) + [st.absmax for st in states] + [st.state2.absmax for st in states])
+    lib.cbnb_set_gemv_host_tables(tabs[0], tabs[1])
+    rc = getattr(lib, f"cgemm_4bit_inference_nested_multi_{_SUFFIX[A.dtype]}")(
+        ct.c_int32(n), (ct.c_int32 * n)(*[st.shape[0] for st in states]), ct.c_int32(k), get_ptr(A),
+        (vp * n)(*[B.data_ptr() for B in Bs]), (vp * n)(*[st.absmax.data_ptr() for st in states]),
+        (vp * n)(*[st.state2.absmax.data_ptr() for st in states]), get_ptr(s0.state2.code), (ct.c_float * n)(*offs),
+        get_ptr(code), (vp * n)(*[o.data_ptr() for o in outs]), ct.c_int32(64), ct.c_int32(s0.state2.blocksize))
+    post_call(prev)
+    if rc != 0:
+        return [gemv_4bit(A, B, out=o, state=st) for B, st, o in zip(Bs, states, outs)]
+    return outs
+
+
 def gemm_4bit(A: Tensor, B: Tensor, state: QuantState, bias: Optional[Tensor] = None,
               out: Optional[Tensor] = None) -> Optional[Tensor]:
     """ADDITIVE: fused batch>1 4-bit GEMM, out[b, N] = A[b, K] @ T(dequant(B))^T (+bias) without ever

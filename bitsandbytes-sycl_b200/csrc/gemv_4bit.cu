@@ -72,6 +72,16 @@ struct GemvArgs {
   // running on the SM and takes 0.6-2.5 us to come back -- on the critical path of every launch.  (Passing the
   // tables by value was measured too: kernel parameters come through the same memory system, no gain.)
   int tables_in_args;
+  // several weight matrices that share x, K and the code tables in ONE launch (q/k/v, gate/up): the tile index space
+  // is the concatenation of the matrices' 16-row tiles; mt[i] = first tile of matrix i (mt[nmat..4] = INT_MAX)
+  int nmat;
+  int mt[5];
+  int mN[4];
+  float moff[4];
+  const unsigned char *mB[4];
+  const unsigned char *mq[4];
+  const float *mam2[4];
+  void *mout[4];
   void *out;                 // [batch, N] T
   // multi-GPU (N-sharded linear): the same output slice is also stored into the peers' copies of the full
   // output vector through NVLink peer mappings -- the all-gather happens in the GEMV epilogue
@@ -527,7 +537,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return v;
 }
 
-template <typename T, bool NESTED, int EXP = 0, int DEPTH = 2, int WARPS = 16>
+template <typename T, bool NESTED, int EXP = 0, int DEPTH = 2, int WARPS = 16, bool MULTI = false>
 __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(const GemvArgs a, int x_blocks_padded, int tiles_total) {
   // shared memory: [0, 64 KB) byte LUT (entry stride 256 B, one word per lane) | code2 | x | partial sums.
   // The lookup address is  LUT base (uniform register) + PRMT(byte << 8 | lane * 4): no alignment requirement.
@@ -584,15 +594,23 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
   const int ntl = t_end - t_begin;
 
   uint32_t w[DEPTH][2][2][8];   // [ring slot][block t / t+4][row half][32 bytes = one sector per lane]
-  struct Abs { uint32_t q[2]; float am2[2]; float2 am[2]; };
+  struct Abs { uint32_t q[2]; float am2[2]; float2 am[2]; float off; };
   Abs ab[DEPTH];
+  // MULTI: which matrix a tile belongs to, and that matrix's operands (select chains: kernel parameters cannot be
+  // indexed dynamically without a copy to local memory)
+  auto mat_of = [&](int tile) { return MULTI ? (int)(tile >= a.mt[1]) + (int)(tile >= a.mt[2]) + (int)(tile >= a.mt[3]) : 0; };
+#define BNB_MSEL(arr, m) ((m) == 0 ? a.arr[0] : (m) == 1 ? a.arr[1] : (m) == 2 ? a.arr[2] : a.arr[3])
 
   // one 256-bit load per (row, block): a lane owns a whole 32-byte sector, 4 lanes one 128-byte line
   auto load_w = [&](uint32_t (&dst)[2][8], int j, int tile, int c) {
+    const int m = mat_of(tile);
+    const int lt = MULTI ? tile - BNB_MSEL(mt, m) : tile;
+    const int Nm = MULTI ? BNB_MSEL(mN, m) : a.N;
+    const unsigned char *Bm = MULTI ? BNB_MSEL(mB, m) : a.B;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-      const int row = min(tile * 16 + g + 8 * h, a.N - 1);
-      const unsigned char *p = a.B + (size_t)row * row_bytes + c * 256 + (t + 4 * j) * 32;
+      const int row = min(lt * 16 + g + 8 * h, Nm - 1);
+      const unsigned char *p = Bm + (size_t)row * row_bytes + c * 256 + (t + 4 * j) * 32;
       if (EXP == 2) {   // experiment: compute only, no global weight traffic
 #pragma unroll
         for (int i = 0; i < 8; i++) dst[h][i] = (uint32_t)(tid * 2654435761u) + i * 0x01010101u + c;
@@ -604,13 +622,19 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
     }
   };
   auto load_abs = [&](Abs &d, int tile, int c) {
+    const int m = mat_of(tile);
+    const int lt = MULTI ? tile - BNB_MSEL(mt, m) : tile;
+    const int Nm = MULTI ? BNB_MSEL(mN, m) : a.N;
+    const unsigned char *qm = MULTI ? BNB_MSEL(mq, m) : a.qabsmax;
+    const float *am2m = MULTI ? BNB_MSEL(mam2, m) : a.absmax2;
+    if (MULTI) d.off = BNB_MSEL(moff, m);
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-      const int row = min(tile * 16 + g + 8 * h, a.N - 1);
+      const int row = min(lt * 16 + g + 8 * h, Nm - 1);
       const size_t idx = (size_t)row * kb + min(c * 8 + 2 * t, kb - 2);
       if (NESTED) {
-        d.q[h] = __ldg(reinterpret_cast<const unsigned short *>(a.qabsmax + idx));
-        d.am2[h] = __ldg(a.absmax2 + (idx >> a.bs2_shift));
+        d.q[h] = __ldg(reinterpret_cast<const unsigned short *>(qm + idx));
+        d.am2[h] = __ldg(am2m + (idx >> a.bs2_shift));
       } else {
         d.am[h] = __ldg(reinterpret_cast<const float2 *>(a.absmax + idx));
       }
@@ -640,11 +664,6 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
   {
     constexpr int CT = WARPS * 32;
     if (probing) g_gemv_probe[7] = globaltimer_ns() - probe_t;      // first weight loads issued
-    // ONE round of global loads for all tables (the 16 code values as four 128-bit loads + this thread's low-nibble
-    // value + its code2 entries); the LUT is then built from registers.  A load per LUT entry costs eight serial L2
-    // round trips here -- 2 us of every launch, on the critical path (measured with the phase probe).
-#pragma unroll
-
     // byte e -> {T(code[e >> 4]), T(code[e & 15])}, replicated for the 32 lanes (bank == lane): 8 threads write
     // one 128-byte entry with conflict-free 128-bit stores.  Thread (tid >> 3) + it * CT/8 handles entries whose low
     // nibble is fixed ((tid >> 3) & 15) and whose high nibble is a compile-time function of `it` plus bits of tid.
@@ -741,10 +760,11 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
       }
       float am00, am01, am10, am11;
       if (NESTED) {
-        am00 = __fadd_rn(__fmul_rn(s_code2[ab[s].q[0] & 0xFFu], ab[s].am2[0]), offset);
-        am01 = __fadd_rn(__fmul_rn(s_code2[ab[s].q[0] >> 8], ab[s].am2[0]), offset);
-        am10 = __fadd_rn(__fmul_rn(s_code2[ab[s].q[1] & 0xFFu], ab[s].am2[1]), offset);
-        am11 = __fadd_rn(__fmul_rn(s_code2[ab[s].q[1] >> 8], ab[s].am2[1]), offset);
+        const float off = MULTI ? ab[s].off : offset;
+        am00 = __fadd_rn(__fmul_rn(s_code2[ab[s].q[0] & 0xFFu], ab[s].am2[0]), off);
+        am01 = __fadd_rn(__fmul_rn(s_code2[ab[s].q[0] >> 8], ab[s].am2[0]), off);
+        am10 = __fadd_rn(__fmul_rn(s_code2[ab[s].q[1] & 0xFFu], ab[s].am2[1]), off);
+        am11 = __fadd_rn(__fmul_rn(s_code2[ab[s].q[1] >> 8], ab[s].am2[1]), off);
       } else {
         am00 = ab[s].am[0].x; am01 = ab[s].am[0].y; am10 = ab[s].am[1].x; am11 = ab[s].am[1].y;
       }
@@ -780,6 +800,12 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
     float sum = 0.f;
 #pragma unroll
     for (int wq = 0; wq < WARPS; wq++) sum += p[wq * 16];
+    if (MULTI) {
+      const int m = mat_of(t_begin + tile_l);
+      const int rr = (t_begin + tile_l - BNB_MSEL(mt, m)) * 16 + row;
+      if (rr < BNB_MSEL(mN, m)) reinterpret_cast<T *>(BNB_MSEL(mout, m))[rr] = from_float<T>(sum);
+      continue;
+    }
     const int r = (t_begin + tile_l) * 16 + row;
     if (r < a.N) {
       const T v = from_float<T>(sum);
@@ -806,6 +832,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
   }
 }
 
+#undef BNB_MSEL
 // ------------------------------------------------------------------------------------------------
 // TMA-staged block-column kernel (the production path for batch 1).
 //
@@ -1600,6 +1627,69 @@ void gemv_4bit_nested(int m, int n, int k, const T *A, const unsigned char *B, c
   }
   launch_mma<T, true>(a, blocksize2);
 }
+
+// Several nested-absmax NF4/FP4 weight matrices that share x (q/k/v, gate/up of a decoder layer) in ONE launch of the
+// block-column kernel: the per-launch constant (table build, dependency wait, x fetch, drain: ~2.7 us) is
+// paid once.  Same arithmetic per output element as the single-matrix call (bit-identical results).
+// returns 0 ok, 1 shape not taken (caller issues the single-matrix calls)
+template <typename T>
+int gemv_4bit_nested_multi(int count, const int *ms, int k, const T *A, const unsigned char *const *Bs,
+                           const unsigned char *const *qabs, const float *const *am2s, const float *code2,
+                           const float *offsets, const float *datatype, T *const *outs, int blocksize, int blocksize2) {
+  if (count < 1 || count > 4 || k <= 0 || blocksize != 64 || (k % 256) != 0 || blocksize2 <= 0 || (blocksize2 & (blocksize2 - 1)) != 0 ||
+      (reinterpret_cast<uintptr_t>(A) % 16) != 0)
+    return 1;
+  GemvArgs a{};
+  a.K = k; a.batch = 1; a.blocksize = blocksize; a.bs_shift = 6; a.bs2_shift = ilog2(blocksize2);
+  a.x = A; a.code2 = code2; a.code = datatype; a.nmat = count;
+  int tiles = 0, nsum = 0;
+  for (int i = 0; i < 5; i++) a.mt[i] = 0x7fffffff;
+  for (int i = 0; i < count; i++) {
+    if (ms[i] <= 0 || (reinterpret_cast<uintptr_t>(Bs[i]) % 8) != 0 || (reinterpret_cast<uintptr_t>(qabs[i]) % 4) != 0) return 1;
+    a.mt[i] = tiles; a.mN[i] = ms[i]; a.moff[i] = offsets[i];
+    a.mB[i] = Bs[i]; a.mq[i] = qabs[i]; a.mam2[i] = am2s[i]; a.mout[i] = outs[i];
+    tiles += ceil_div(ms[i], 16); nsum += ms[i];
+  }
+  for (int i = count; i < 4; i++) { a.mN[i] = 1; a.mB[i] = Bs[0]; a.mq[i] = qabs[0]; a.mam2[i] = am2s[0]; a.mout[i] = outs[0]; }
+  a.N = nsum; a.B = Bs[0]; a.qabsmax = qabs[0]; a.absmax2 = am2s[0]; a.offset = offsets[0]; a.out = outs[0];
+  if (tl_code_host != nullptr) {
+    static const float nf4[16] = BNB_NF4_TABLE;
+    bool same = true;
+    for (int i = 0; i < 16; i++) same = same && (tl_code_host[i] == nf4[i]);
+    if (same) a.tables_in_args = 2;
+  }
+  tl_code_host = tl_code2_host = nullptr;
+  int dev = 0, sms = kNumSMs;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int xblocks = ceil_div(k, 512) * 8;
+  auto smem_need = [&](int warps, int grid) {
+    return (size_t)65536 + kBcHead + (size_t)xblocks * kBcXPitch + (size_t)ceil_div(tiles, grid) * warps * 16 * sizeof(float);
+  };
+  int warps = 8, grid = tiles < sms * 2 ? tiles : sms * 2;
+  if (smem_need(warps, grid) > (size_t)(113 * 1024)) { warps = 16; grid = tiles < sms ? tiles : sms; }
+  const size_t need = smem_need(warps, grid);
+  if (need > (size_t)kBcSmemMax) return 1;
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(grid); lc.blockDim = dim3(warps * 32); lc.dynamicSmemBytes = need; lc.stream = current_stream();
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr; lc.numAttrs = 1;
+  if (warps == 8) {
+    auto kfn = k_gemv4_bc<T, true, 0, 2, 8, true>;
+    latch_error(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kBcSmemMax), "gemv multi smem attr");
+    latch_error(cudaLaunchKernelEx(&lc, kfn, a, xblocks, tiles), "gemv_4bit (multi) launch");
+  } else {
+    auto kfn = k_gemv4_bc<T, true, 0, 2, 16, true>;
+    latch_error(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kBcSmemMax), "gemv multi smem attr");
+    latch_error(cudaLaunchKernelEx(&lc, kfn, a, xblocks, tiles), "gemv_4bit (multi) launch");
+  }
+  check_launch("gemv_4bit (multi)");
+  return 0;
+}
+template int gemv_4bit_nested_multi<__half>(int, const int *, int, const __half *, const unsigned char *const *, const unsigned char *const *, const float *const *, const float *, const float *, const float *, __half *const *, int, int);
+template int gemv_4bit_nested_multi<__nv_bfloat16>(int, const int *, int, const __nv_bfloat16 *, const unsigned char *const *, const unsigned char *const *, const float *const *, const float *, const float *, const float *, __nv_bfloat16 *const *, int, int);
 
 template void gemv_4bit<float>(int, int, int, const float *, const unsigned char *, const float *, const float *, float *, int, int, int, int);
 template void gemv_4bit<__half>(int, int, int, const __half *, const unsigned char *, const float *, const float *, __half *, int, int, int, int);

@@ -125,6 +125,14 @@ BNB_B200_API void cbnb_debug_gemv_probe(unsigned long long *cycles_ns);
 /* GEMV with the NESTED (double-quantised) absmax consumed directly: qabsmax uint8 [N*K/blocksize],
  * absmax2 fp32 [ceil(nblocks/blocksize2)], code2 fp32[256], offset scalar. De-nesting is
  * fl(fl(code2[q] * absmax2[i / blocksize2]) + offset), identical to functional.py:1982-1984. */
+/* Up to four nested-absmax 4-bit weight matrices that SHARE the activation vector, K and the code tables (q/k/v or
+ * gate/up of a decoder layer) in one launch: out_i[0..m_i) = B_i[m_i, k] . A.  m, offsets: HOST arrays of `count`
+ * entries; B, qabsmax, absmax2, outs: HOST arrays of `count` device pointers; code2 / datatype: device, shared by all
+ * matrices.  Results are bit-identical to `count` calls of cgemm_4bit_inference_nested_*; the per-launch constant
+ * (~2.7 us on a B200) is paid once.  Returns 0 ok, 1 shape not taken (issue the single calls instead). */
+BNB_B200_API int cgemm_4bit_inference_nested_multi_fp16(int count, const int *m, int k, void *A, unsigned char **B, unsigned char **qabsmax, float **absmax2, float *code2, const float *offsets, float *datatype, void **outs, int blocksize, int blocksize2);
+BNB_B200_API int cgemm_4bit_inference_nested_multi_bf16(int count, const int *m, int k, void *A, unsigned char **B, unsigned char **qabsmax, float **absmax2, float *code2, const float *offsets, float *datatype, void **outs, int blocksize, int blocksize2);
+
 /* Optional, per thread, consumed by the NEXT cgemm_4bit_inference_nested[_push]_* call: HOST copies of that call's
  * `datatype` (16 floats) and `code2` (256 floats; may be NULL).  When the host copy equals the NF4 table the kernel
  * builds its lookup table from immediates instead of waiting for a global load (which queues behind the weight

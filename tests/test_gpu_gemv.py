@@ -210,3 +210,24 @@ def test_experimental_gemv_kernels_stay_parity_green(impl):
     env = dict(os.environ, BNB_B200_GEMV_IMPL=impl)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("Ns,K", [((4096, 4096, 4096), 4096), ((11008, 11008), 4096), ((100, 4096, 24, 1000), 1024), ((512,), 11008)])
+def test_gemv_multi_is_bit_identical_to_single_calls(F, dtype, Ns, K):
+    """ADDITIVE cgemm_4bit_inference_nested_multi_*: the matrices of a decoder layer that share x (q/k/v, gate/up) in one
+    launch.  Same arithmetic per output element -> every output bit equals the single-matrix call's."""
+    torch.manual_seed(len(Ns) * 1000 + K)
+    x = torch.randn(1, K).to(DT[dtype]).cuda()
+    qs, sts = [], []
+    for i, N in enumerate(Ns):
+        W = (torch.randn(N, K) * (0.02 + 0.01 * i)).to(DT[dtype]).cuda()
+        q, st = F.quantize_4bit(W, blocksize=64, compress_statistics=True, quant_type="nf4")
+        qs.append(q)
+        sts.append(st)
+    singles = [F.gemv_4bit(x, q.t(), state=st) for q, st in zip(qs, sts)]
+    multi = F.gemv_4bit_multi(x, [q.t() for q in qs], sts)
+    torch.cuda.synchronize()
+    for a, b, N in zip(singles, multi, Ns):
+        assert b.shape == (1, N)
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16)), N
