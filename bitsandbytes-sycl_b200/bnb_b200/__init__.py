@@ -2,7 +2,7 @@
 of abhilash1910/bitsandbytes-SYCL's `python_src_quants` package (reference __init__.py:3-11):
 `functional`, `matmul`, `matmul_4bit`, `MatmulLtState`, `nn.Linear4bit`, `nn.Linear8bitLt`."""
 from . import functional, utils  # noqa: F401
-from .autograd._functions import MatmulLtState, matmul, matmul_4bit  # noqa: F401
+from .autograd._functions import MatmulLtState, matmul, matmul_4bit, matmul_4bit_multi  # noqa: F401
 from .nn import modules  # noqa: F401
 from . import nn  # noqa: F401
 

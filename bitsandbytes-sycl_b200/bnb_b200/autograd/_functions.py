@@ -274,3 +274,20 @@ def matmul_4bit(A: torch.Tensor, B: torch.Tensor, quant_state: F.QuantState, out
             out += bias
         return out
     return MatMul4Bit.apply(A, B, out, bias, quant_state)
+
+
+def matmul_4bit_multi(A: torch.Tensor, Bs, quant_states, outs=None, biases=None):
+    """ADDITIVE (inference): matmul_4bit for several 4-bit weights that share the activation row A -- the q/k/v or
+    gate/up projections of a decoder layer -- in one GEMV launch (functional.gemv_4bit_multi).  Falls back to one
+    matmul_4bit per weight whenever matmul_4bit itself would not take the GEMV route (batch > 1, gradients, K not a
+    multiple of the blocksize)."""
+    n = len(Bs)
+    outs = list(outs) if outs is not None else [None] * n
+    biases = list(biases) if biases is not None else [None] * n
+    if A.numel() == A.shape[-1] and A.requires_grad == False and all(A.shape[-1] % st.blocksize == 0 for st in quant_states):  # noqa: E712
+        res = F.gemv_4bit_multi(A, [B.t() for B in Bs], quant_states, outs=outs)
+        for r, b in zip(res, biases):
+            if b is not None:
+                r += b
+        return res
+    return [matmul_4bit(A, B, st, out=o, bias=b) for B, st, o, b in zip(Bs, quant_states, outs, biases)]

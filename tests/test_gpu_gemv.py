@@ -231,3 +231,22 @@ def test_gemv_multi_is_bit_identical_to_single_calls(F, dtype, Ns, K):
     for a, b, N in zip(singles, multi, Ns):
         assert b.shape == (1, N)
         assert torch.equal(a.view(torch.int16), b.view(torch.int16)), N
+
+
+def test_matmul_4bit_multi_matches_linear4bit_modules(F):
+    """bnb_b200.matmul_4bit_multi over three LinearNF4 modules (q/k/v style, with bias) == the modules' own forward."""
+    import bnb_b200
+    torch.manual_seed(31)
+    k = 1024
+    lins = [bnb_b200.nn.LinearNF4(k, n, bias=True, compute_dtype=torch.bfloat16).cuda() for n in (1024, 256, 256)]
+    x = torch.randn(1, k, device="cuda", dtype=torch.bfloat16)
+    with torch.no_grad():
+        ref = [lin(x) for lin in lins]
+        got = bnb_b200.matmul_4bit_multi(x, [lin.weight.t() for lin in lins], [lin.weight.quant_state for lin in lins],
+                                         biases=[lin.bias.to(torch.bfloat16) for lin in lins])
+        x8 = torch.randn(8, k, device="cuda", dtype=torch.bfloat16)          # batch > 1: per-weight fallback
+        ref8 = [lin(x8) for lin in lins]
+        got8 = bnb_b200.matmul_4bit_multi(x8, [lin.weight.t() for lin in lins], [lin.weight.quant_state for lin in lins],
+                                          biases=[lin.bias.to(torch.bfloat16) for lin in lins])
+    for a, b in zip(ref + ref8, got + got8):
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16))
