@@ -210,6 +210,8 @@ def main():
     ap.add_argument("--sync", default="barrier", choices=["kernel", "barrier"],
                     help="N>1 fused collective: ordering folded into the GEMV kernels, or one symmetric-memory barrier launch per consumer group")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph of the step")
+    ap.add_argument("--no-fuse-same-input", dest="fuse_same_input", action="store_false",
+                    help="N>1: one launch per linear instead of one per group of linears that read the same x (q/k/v, gate/up)")
     ap.add_argument("--graph-shape", default="chain", choices=["decoder", "chain"],
                     help="N=1: dependency structure of the step. chain = all launches on one stream, overlapped by "
                          "programmatic dependent launch (default, measured faster: 2392 vs 2148 GB/s); decoder = the "
@@ -332,7 +334,22 @@ def main():
                     join.record(side_streams[j - 1])
                     main.wait_event(join)
 
+    fuse_sharded = peers is not None and not kernel_sync and per_layer == 7 and args.fuse_same_input
+    if fuse_sharded:
+        from bnb_b200.parallel import sharded_gemv_push_multi
+        collective += "; q/k/v and gate/up share one launch"
+
     def step_eager():
+        if fuse_sharded:     # N-sharded: one launch per group of linears that read the same x, one barrier per group
+            for base in range(0, len(mats), per_layer):
+                for grp in decoder_groups:
+                    ids = [base + p for p in grp]
+                    if len(ids) == 1:
+                        sharded_gemv_push(xs[ids[0]], mats[ids[0]][0], mats[ids[0]][1], peers, ids[0])
+                    else:
+                        sharded_gemv_push_multi(xs[ids[0]], [mats[i][0] for i in ids], [mats[i][1] for i in ids], peers, ids)
+                    peers.barrier()
+            return
         if structured and B == 1:
             run_structured(lambda i: F.gemv_4bit(xs[i], mats[i][0].t(), out=outs[i], state=mats[i][1]))
             return

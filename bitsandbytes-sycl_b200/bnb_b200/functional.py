@@ -529,7 +529,7 @@ def gemv_4bit(A: Tensor, B: Tensor, out: Optional[Tensor] = None, transposed_A=F
     return out
 
 
-def gemv_4bit_multi(A: Tensor, Bs, states, outs=None):
+def gemv_4bit_multi(A: Tensor, Bs, states, outs=None, peer_outs=None):
     """ADDITIVE: out_i = A @ dequant(B_i)^T for up to four nested-absmax 4-bit weights that share the activation row A
     (q/k/v, gate/up of a decoder layer) in ONE launch.  Bit-identical to gemv_4bit per matrix; falls back to the single
     calls for shapes the native path does not take.  Bs: packed weights as passed to gemv_4bit (already .t()-viewed)."""
@@ -547,7 +547,8 @@ def gemv_4bit_multi(A: Tensor, Bs, states, outs=None):
             same = s0._multi_code2_checked = all(torch.equal(st.state2.code, s0.state2.code) for st in states[1:])
         ok = same
     if not ok:
-        return [gemv_4bit(A, B, out=o, state=st) for B, st, o in zip(Bs, states, outs)]
+        return [gemv_4bit(A, B, out=o, state=st, peer_outs=(peer_outs[i] if peer_outs else None))
+                for i, (B, st, o) in enumerate(zip(Bs, states, outs))]
     _require_cuda(A, "gemv_4bit_multi")
     A = A.contiguous()
     k = s0.shape[1]
@@ -571,14 +572,21 @@ def gemv_4bit_multi(A: Tensor, Bs, states, outs=None):
     prev = pre_call(A.device)
     is_on_gpu([A, code, s0.state2.code] + list(Bs) + list(outs) + [st.absmax for st in states] + [st.state2.absmax for st in states])
     lib.cbnb_set_gemv_host_tables(tabs[0], tabs[1])
-    rc = getattr(lib, f"cgemm_4bit_inference_nested_multi_{_SUFFIX[A.dtype]}")(
-        ct.c_int32(n), (ct.c_int32 * n)(*[st.shape[0] for st in states]), ct.c_int32(k), get_ptr(A),
-        (vp * n)(*[B.data_ptr() for B in Bs]), (vp * n)(*[st.absmax.data_ptr() for st in states]),
-        (vp * n)(*[st.state2.absmax.data_ptr() for st in states]), get_ptr(s0.state2.code), (ct.c_float * n)(*offs),
-        get_ptr(code), (vp * n)(*[o.data_ptr() for o in outs]), ct.c_int32(64), ct.c_int32(s0.state2.blocksize))
+    common = (ct.c_int32(n), (ct.c_int32 * n)(*[st.shape[0] for st in states]), ct.c_int32(k), get_ptr(A),
+              (vp * n)(*[B.data_ptr() for B in Bs]), (vp * n)(*[st.absmax.data_ptr() for st in states]),
+              (vp * n)(*[st.state2.absmax.data_ptr() for st in states]), get_ptr(s0.state2.code), (ct.c_float * n)(*offs),
+              get_ptr(code), (vp * n)(*[o.data_ptr() for o in outs]), ct.c_int32(64), ct.c_int32(s0.state2.blocksize))
+    if peer_outs:   # N-sharded: [matrix][peer] peer-mapped addresses of the output slices
+        npeers = len(peer_outs[0])
+        flat = [int(p) for po in peer_outs for p in po]
+        rc = getattr(lib, f"cgemm_4bit_inference_nested_multi_push_{_SUFFIX[A.dtype]}")(
+            *common, (vp * len(flat))(*flat), ct.c_int32(npeers))
+    else:
+        rc = getattr(lib, f"cgemm_4bit_inference_nested_multi_{_SUFFIX[A.dtype]}")(*common)
     post_call(prev)
     if rc != 0:
-        return [gemv_4bit(A, B, out=o, state=st) for B, st, o in zip(Bs, states, outs)]
+        return [gemv_4bit(A, B, out=o, state=st, peer_outs=(peer_outs[i] if peer_outs else None))
+                for i, (B, st, o) in enumerate(zip(Bs, states, outs))]
     return outs
 
 

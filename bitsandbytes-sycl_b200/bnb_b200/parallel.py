@@ -173,3 +173,10 @@ def sharded_gemv_push(x: torch.Tensor, packed_shard: torch.Tensor, state_shard: 
     """Rank-local GEMV of linear i whose epilogue stores the output slice into every rank's full vector."""
     return F.gemv_4bit(x, packed_shard.t(), out=peers.local_slice(i), state=state_shard, peer_outs=peers.peer_ptrs(i),
                        sync=sync)
+
+
+def sharded_gemv_push_multi(x: torch.Tensor, packed_shards, state_shards, peers: PeerOutputBuffers, idxs) -> list:
+    """The linears `idxs` of a layer that share x (q/k/v, gate/up), rank-local slices, in ONE launch whose epilogue
+    stores every slice into every rank's full vectors (functional.gemv_4bit_multi with peer outputs)."""
+    return F.gemv_4bit_multi(x, [p.t() for p in packed_shards], state_shards, outs=[peers.local_slice(i) for i in idxs],
+                             peer_outs=[peers.peer_ptrs(i) for i in idxs])

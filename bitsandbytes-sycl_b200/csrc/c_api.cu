@@ -29,7 +29,7 @@ template <typename T, int QT> void dequantize_blockwise(const float *, const uns
 long long selftest_quant_lut(int qtype);
 void gemv_probe(unsigned long long *out2);
 void set_gemv_host_tables(const float *code16, const float *code2_256);
-template <typename T> int gemv_4bit_nested_multi(int, const int *, int, const T *, const unsigned char *const *, const unsigned char *const *, const float *const *, const float *, const float *, const float *, T *const *, int, int);
+template <typename T> int gemv_4bit_nested_multi(int, const int *, int, const T *, const unsigned char *const *, const unsigned char *const *, const float *const *, const float *, const float *, const float *, T *const *, int, int, void *const *, int);
 template <typename T> void gemv_4bit(int, int, int, const T *, const unsigned char *, const float *, const float *, T *, int, int, int, int);
 struct GemvSync;
 void epoch_bump(unsigned int *epoch);
@@ -66,9 +66,13 @@ const char *cbnb_version(void) { return "bnb_b200 sm_100a r1"; }
 long long cbnb_selftest_quant_lut(int qtype) { return selftest_quant_lut(qtype); }
 void cbnb_debug_gemv_probe(unsigned long long *cycles_ns) { gemv_probe(cycles_ns); }
 int cgemm_4bit_inference_nested_multi_fp16(int count, const int *m, int k, void *A, unsigned char **B, unsigned char **qabsmax, float **absmax2, float *code2, const float *offsets, float *datatype, void **outs, int blocksize, int blocksize2) {
-  return gemv_4bit_nested_multi<half_t>(count, m, k, (half_t *)A, B, qabsmax, absmax2, code2, offsets, datatype, (half_t *const *)outs, blocksize, blocksize2); }
+  return gemv_4bit_nested_multi<half_t>(count, m, k, (half_t *)A, B, qabsmax, absmax2, code2, offsets, datatype, (half_t *const *)outs, blocksize, blocksize2, nullptr, 0); }
 int cgemm_4bit_inference_nested_multi_bf16(int count, const int *m, int k, void *A, unsigned char **B, unsigned char **qabsmax, float **absmax2, float *code2, const float *offsets, float *datatype, void **outs, int blocksize, int blocksize2) {
-  return gemv_4bit_nested_multi<bf16_t>(count, m, k, (bf16_t *)A, B, qabsmax, absmax2, code2, offsets, datatype, (bf16_t *const *)outs, blocksize, blocksize2); }
+  return gemv_4bit_nested_multi<bf16_t>(count, m, k, (bf16_t *)A, B, qabsmax, absmax2, code2, offsets, datatype, (bf16_t *const *)outs, blocksize, blocksize2, nullptr, 0); }
+int cgemm_4bit_inference_nested_multi_push_fp16(int count, const int *m, int k, void *A, unsigned char **B, unsigned char **qabsmax, float **absmax2, float *code2, const float *offsets, float *datatype, void **outs, int blocksize, int blocksize2, void **peer_outs, int npeers) {
+  return gemv_4bit_nested_multi<half_t>(count, m, k, (half_t *)A, B, qabsmax, absmax2, code2, offsets, datatype, (half_t *const *)outs, blocksize, blocksize2, peer_outs, npeers); }
+int cgemm_4bit_inference_nested_multi_push_bf16(int count, const int *m, int k, void *A, unsigned char **B, unsigned char **qabsmax, float **absmax2, float *code2, const float *offsets, float *datatype, void **outs, int blocksize, int blocksize2, void **peer_outs, int npeers) {
+  return gemv_4bit_nested_multi<bf16_t>(count, m, k, (bf16_t *)A, B, qabsmax, absmax2, code2, offsets, datatype, (bf16_t *const *)outs, blocksize, blocksize2, peer_outs, npeers); }
 void cbnb_set_gemv_host_tables(const float *code16_host, const float *code2_256_host) { set_gemv_host_tables(code16_host, code2_256_host); }
 
 // ---------------------------------------------------------------- blockwise quantize (pythonInterface.cpp:203-217)

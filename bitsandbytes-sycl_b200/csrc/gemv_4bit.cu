@@ -82,6 +82,7 @@ struct GemvArgs {
   const unsigned char *mq[4];
   const float *mam2[4];
   void *mout[4];
+  void *mpeer[4][7];         // MULTI + N-sharding: peer-mapped copies of each matrix's output slice
   void *out;                 // [batch, N] T
   // multi-GPU (N-sharded linear): the same output slice is also stored into the peers' copies of the full
   // output vector through NVLink peer mappings -- the all-gather happens in the GEMV epilogue
@@ -803,7 +804,14 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
     if (MULTI) {
       const int m = mat_of(t_begin + tile_l);
       const int rr = (t_begin + tile_l - BNB_MSEL(mt, m)) * 16 + row;
-      if (rr < BNB_MSEL(mN, m)) reinterpret_cast<T *>(BNB_MSEL(mout, m))[rr] = from_float<T>(sum);
+      if (rr < BNB_MSEL(mN, m)) {
+        const T v = from_float<T>(sum);
+        reinterpret_cast<T *>(BNB_MSEL(mout, m))[rr] = v;
+#pragma unroll
+        for (int pr = 0; pr < 7; pr++)                                       // NVLink P2P stores
+          if (pr < a.npeers)
+            reinterpret_cast<T *>(m == 0 ? a.mpeer[0][pr] : m == 1 ? a.mpeer[1][pr] : m == 2 ? a.mpeer[2][pr] : a.mpeer[3][pr])[rr] = v;
+      }
       continue;
     }
     const int r = (t_begin + tile_l) * 16 + row;
@@ -1635,7 +1643,9 @@ void gemv_4bit_nested(int m, int n, int k, const T *A, const unsigned char *B, c
 template <typename T>
 int gemv_4bit_nested_multi(int count, const int *ms, int k, const T *A, const unsigned char *const *Bs,
                            const unsigned char *const *qabs, const float *const *am2s, const float *code2,
-                           const float *offsets, const float *datatype, T *const *outs, int blocksize, int blocksize2) {
+                           const float *offsets, const float *datatype, T *const *outs, int blocksize, int blocksize2,
+                           void *const *peer_outs, int npeers) {
+  if (npeers < 0 || npeers > 7 || (npeers > 0 && peer_outs == nullptr)) return 1;
   if (count < 1 || count > 4 || k <= 0 || blocksize != 64 || (k % 256) != 0 || blocksize2 <= 0 || (blocksize2 & (blocksize2 - 1)) != 0 ||
       (reinterpret_cast<uintptr_t>(A) % 16) != 0)
     return 1;
@@ -1651,6 +1661,9 @@ int gemv_4bit_nested_multi(int count, const int *ms, int k, const T *A, const un
     tiles += ceil_div(ms[i], 16); nsum += ms[i];
   }
   for (int i = count; i < 4; i++) { a.mN[i] = 1; a.mB[i] = Bs[0]; a.mq[i] = qabs[0]; a.mam2[i] = am2s[0]; a.mout[i] = outs[0]; }
+  a.npeers = npeers;
+  for (int i = 0; i < count; i++)
+    for (int p = 0; p < npeers; p++) a.mpeer[i][p] = peer_outs[i * npeers + p];     // matrix-major
   a.N = nsum; a.B = Bs[0]; a.qabsmax = qabs[0]; a.absmax2 = am2s[0]; a.offset = offsets[0]; a.out = outs[0];
   if (tl_code_host != nullptr) {
     static const float nf4[16] = BNB_NF4_TABLE;
@@ -1688,8 +1701,8 @@ int gemv_4bit_nested_multi(int count, const int *ms, int k, const T *A, const un
   check_launch("gemv_4bit (multi)");
   return 0;
 }
-template int gemv_4bit_nested_multi<__half>(int, const int *, int, const __half *, const unsigned char *const *, const unsigned char *const *, const float *const *, const float *, const float *, const float *, __half *const *, int, int);
-template int gemv_4bit_nested_multi<__nv_bfloat16>(int, const int *, int, const __nv_bfloat16 *, const unsigned char *const *, const unsigned char *const *, const float *const *, const float *, const float *, const float *, __nv_bfloat16 *const *, int, int);
+template int gemv_4bit_nested_multi<__half>(int, const int *, int, const __half *, const unsigned char *const *, const unsigned char *const *, const float *const *, const float *, const float *, const float *, __half *const *, int, int, void *const *, int);
+template int gemv_4bit_nested_multi<__nv_bfloat16>(int, const int *, int, const __nv_bfloat16 *, const unsigned char *const *, const unsigned char *const *, const float *const *, const float *, const float *, const float *, __nv_bfloat16 *const *, int, int, void *const *, int);
 
 template void gemv_4bit<float>(int, int, int, const float *, const unsigned char *, const float *, const float *, float *, int, int, int, int);
 template void gemv_4bit<__half>(int, int, int, const __half *, const unsigned char *, const float *, const float *, __half *, int, int, int, int);

@@ -133,6 +133,11 @@ BNB_B200_API void cbnb_debug_gemv_probe(unsigned long long *cycles_ns);
 BNB_B200_API int cgemm_4bit_inference_nested_multi_fp16(int count, const int *m, int k, void *A, unsigned char **B, unsigned char **qabsmax, float **absmax2, float *code2, const float *offsets, float *datatype, void **outs, int blocksize, int blocksize2);
 BNB_B200_API int cgemm_4bit_inference_nested_multi_bf16(int count, const int *m, int k, void *A, unsigned char **B, unsigned char **qabsmax, float **absmax2, float *code2, const float *offsets, float *datatype, void **outs, int blocksize, int blocksize2);
 
+/* Same, N-sharded: every output slice is also stored into the peers' copies (peer_outs: HOST array of count * npeers
+ * peer-mapped device addresses, matrix-major), as cgemm_4bit_inference_nested_push_* does for one matrix. */
+BNB_B200_API int cgemm_4bit_inference_nested_multi_push_fp16(int count, const int *m, int k, void *A, unsigned char **B, unsigned char **qabsmax, float **absmax2, float *code2, const float *offsets, float *datatype, void **outs, int blocksize, int blocksize2, void **peer_outs, int npeers);
+BNB_B200_API int cgemm_4bit_inference_nested_multi_push_bf16(int count, const int *m, int k, void *A, unsigned char **B, unsigned char **qabsmax, float **absmax2, float *code2, const float *offsets, float *datatype, void **outs, int blocksize, int blocksize2, void **peer_outs, int npeers);
+
 /* Optional, per thread, consumed by the NEXT cgemm_4bit_inference_nested[_push]_* call: HOST copies of that call's
  * `datatype` (16 floats) and `code2` (256 floats; may be NULL).  When the host copy equals the NF4 table the kernel
  * builds its lookup table from immediates instead of waiting for a global load (which queues behind the weight

@@ -55,6 +55,28 @@ for it in range(4):
         if not (same and same_nccl):
             ok = False
             print(f"rank {rank} iter {it} shape {shapes[i]}: fused {same} nccl {same_nccl}", flush=True)
+# ---- several linears that share x in ONE launch (q/k/v style: three matrices, same K, same x), fused all-gather
+from bnb_b200.parallel import sharded_gemv_push_multi  # noqa: E402
+mshapes = [(4096, 4096), (1024, 4096), (1024, 4096)]
+mfull, mshards = [], []
+for (N, K) in mshapes:
+    W = (torch.randn(N, K, device=dev) * 0.02).bfloat16()
+    q, st = F.quantize_4bit(W, blocksize=64, compress_statistics=True, quant_type="nf4")
+    mfull.append((q, st))
+    mshards.append(shard_quantized_weight(q, st, world, rank))
+xm = torch.randn(1, 4096, device=dev).bfloat16()
+mpeers = PeerOutputBuffers([N for (N, _) in mshapes], torch.bfloat16, dev)
+mpeers.buf.zero_()
+dist.barrier()
+torch.cuda.synchronize()
+sharded_gemv_push_multi(xm, [s[0] for s in mshards], [s[1] for s in mshards], mpeers, [0, 1, 2])
+mpeers.barrier()
+torch.cuda.synchronize()
+for i, (q, st) in enumerate(mfull):
+    ref = F.gemv_4bit(xm, q.t(), state=st)
+    if not torch.equal(ref.view(torch.int16), mpeers.full(i).view(torch.int16)):
+        ok = False
+        print(f"rank {rank} multi-launch shape {mshapes[i]}: MISMATCH", flush=True)
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
