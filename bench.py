@@ -210,6 +210,8 @@ def main():
     ap.add_argument("--sync", default="barrier", choices=["kernel", "barrier"],
                     help="N>1 fused collective: ordering folded into the GEMV kernels, or one symmetric-memory barrier launch per consumer group")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph of the step")
+    ap.add_argument("--barrier", default="pdl", choices=["pdl", "symm"],
+                    help="N>1: consumer-group barrier = cbnb_peer_barrier (a link of the PDL chain) or torch symmetric-memory barrier")
     ap.add_argument("--no-fuse-same-input", dest="fuse_same_input", action="store_false",
                     help="N>1: one launch per linear instead of one per group of linears that read the same x (q/k/v, gate/up)")
     ap.add_argument("--graph-shape", default="chain", choices=["decoder", "chain"],
@@ -276,6 +278,9 @@ def main():
                 from bnb_b200.parallel import PeerOutputBuffers, sharded_gemv_push
                 peers = PeerOutputBuffers([N for (_, _, N, _) in mats], dtype, dev)
                 collective = "fused-epilogue-p2p-stores+symm-barrier-per-consumer-group"
+                if args.barrier == "pdl" and args.sync != "kernel":
+                    peers.enable_fast_barrier()
+                    collective = "fused-epilogue-p2p-stores+pdl-chained-peer-barrier-per-consumer-group"
                 if args.sync == "kernel":
                     peers.enable_kernel_sync(ngroups=args.layers * 4 if len(shapes) == 7 else len(mats))
                     collective = "fused-epilogue-p2p-stores+in-kernel-signal/wait-per-consumer-group"

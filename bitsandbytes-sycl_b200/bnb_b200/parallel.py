@@ -128,7 +128,32 @@ class PeerOutputBuffers:
         return [self.base_ptrs[p] + o for p in range(self.world) if p != self.rank]
 
     def barrier(self, channel: int = 0) -> None:
-        self.hdl.barrier(channel=channel)
+        if getattr(self, "_fb", None) is not None:
+            self.fast_barrier()
+        else:
+            self.hdl.barrier(channel=channel)
+
+    # ---- barrier as a link of the PDL chain (cbnb_peer_barrier): the next GEMV's prologue overlaps the exchange
+    def enable_fast_barrier(self) -> None:
+        import ctypes as ct
+        import torch.distributed._symmetric_memory as symm_mem
+
+        sig = symm_mem.empty(64, dtype=torch.int32, device=self.buf.device)
+        sig.zero_()
+        hdl = symm_mem.rendezvous(sig, self.group)
+        counter = torch.zeros(1, dtype=torch.int32, device=self.buf.device)
+        torch.cuda.synchronize()
+        hdl.barrier(channel=0)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        others = [p for p in range(self.world) if p != self.rank]
+        mine = [ptrs[p] + 4 * (self.rank if self.rank < p else self.rank - 1) for p in others]   # my compact slot at peer p
+        self._fb = (sig, hdl, counter, (ct.c_void_p * len(mine))(*mine), len(mine))
+
+    def fast_barrier(self) -> None:
+        import ctypes as ct
+        sig, _, counter, arr, n = self._fb
+        F.lib.cbnb_set_stream(ct.c_void_p(torch.cuda.current_stream().cuda_stream))
+        F.lib.cbnb_peer_barrier(ct.c_void_p(counter.data_ptr()), ct.c_void_p(sig.data_ptr()), arr, ct.c_int32(n))
 
     # ---- in-kernel ordering (no barrier launch): signal slots in symmetric memory + a per-pass epoch
     def enable_kernel_sync(self, ngroups: int) -> None:

@@ -33,6 +33,7 @@ template <typename T> int gemv_4bit_nested_multi(int, const int *, int, const T 
 template <typename T> void gemv_4bit(int, int, int, const T *, const unsigned char *, const float *, const float *, T *, int, int, int, int);
 struct GemvSync;
 void epoch_bump(unsigned int *epoch);
+void peer_barrier(unsigned int *counter, const unsigned int *sig_local, unsigned int *const *sig_peer, int npeers);
 template <typename T> void gemv_4bit_nested(int, int, int, const T *, const unsigned char *, const unsigned char *, const float *, const float *, float, const float *, T *, int, int, int, int, int, void *const *, int, const GemvSync *);
 template <typename T> int gemm_4bit(int, int, int, const T *, const unsigned char *, const float *, const float *, const T *, T *, int);
 void get_col_row_stats(const __half *, float *, float *, int *, float, int, int);
@@ -117,6 +118,7 @@ void cgemm_4bit_inference_nested_push_fp16(int m, int n, int k, void *A, unsigne
 void cgemm_4bit_inference_nested_push_bf16(int m, int n, int k, void *A, unsigned char *B, unsigned char *qabsmax, float *absmax2, float *code2, float offset, float *datatype, void *out, int lda, int ldb, int ldc, int blocksize, int blocksize2, void **peer_outs, int npeers, const bnb_gemv_sync_t *sync) {
   gemv_4bit_nested<bf16_t>(m, n, k, (bf16_t *)A, B, qabsmax, absmax2, code2, offset, datatype, (bf16_t *)out, lda, ldb, ldc, blocksize, blocksize2, peer_outs, npeers, reinterpret_cast<const GemvSync *>(sync)); }
 void cbnb_epoch_bump(unsigned int *epoch) { epoch_bump(epoch); }
+void cbnb_peer_barrier(unsigned int *counter, const unsigned int *sig_local, unsigned int **sig_peer, int npeers) { peer_barrier(counter, sig_local, sig_peer, npeers); }
 
 // ---------------------------------------------------------------- fused 4-bit GEMM (additive)
 int cgemm_4bit_fp16(int batch, int N, int K, void *A, unsigned char *B, float *absmax, float *datatype, void *bias, void *out, int blocksize) {

@@ -530,6 +530,41 @@ void epoch_bump(unsigned int *epoch) {
   check_launch("epoch_bump");
 }
 
+// Cross-GPU barrier of an N-sharded stack as a link of the programmatic-dependent-launch chain: it lets the NEXT
+// kernel's CTAs start (tables, weight prefetch) at once, waits for the previous kernel of the stream -- the GEMV whose
+// epilogue stored into the peers -- and then exchanges one sequence number with every peer through symmetric memory.
+// The library barrier of torch's symmetric memory is an ordinary launch: it serialises both neighbours (~8 us per
+// consumer group on the 7B stack).  seq lives on the device, so a replayed CUDA graph keeps counting.
+struct PeerSlots { unsigned int *p[7]; };
+__global__ void __launch_bounds__(32) k_peer_barrier(unsigned int *counter, const unsigned int *sig_local, PeerSlots peers, int npeers) {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  unsigned int seq = 0;
+  if (threadIdx.x == 0) { seq = *counter + 1u; *counter = seq; }
+  seq = __shfl_sync(0xffffffffu, seq, 0);
+  if ((int)threadIdx.x < npeers) {
+    __threadfence_system();                           // the previous kernel's peer stores are ordered before the flag
+    st_release_sys(peers.p[threadIdx.x], seq);
+    const unsigned int *slot = sig_local + threadIdx.x;
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(slot) - seq) < 0) {
+      if (clock64() - t0 > 4000000000ll) __trap();    // bounded spin: trap, never hang
+    }
+  }
+}
+void peer_barrier(unsigned int *counter, const unsigned int *sig_local, unsigned int *const *sig_peer, int npeers) {
+  if (npeers < 0 || npeers > 7) { latch_error(cudaErrorInvalidValue, "peer_barrier: at most 7 peers"); return; }
+  PeerSlots ps{};
+  for (int i = 0; i < npeers; i++) ps.p[i] = sig_peer[i];
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(1); lc.blockDim = dim3(32); lc.dynamicSmemBytes = 0; lc.stream = current_stream();
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr; lc.numAttrs = 1;
+  latch_error(cudaLaunchKernelEx(&lc, k_peer_barrier, counter, sig_local, ps, npeers), "peer_barrier launch");
+}
+
 // debug probe (flags bit 1): SM cycles and nanoseconds spent by CTA 0 -> effective SM clock under this kernel's load
 __device__ unsigned long long g_gemv_probe[12];   // [0] cycles, [1] ns of the probed CTA; [2..6] phase timestamps (ns since entry)
 __device__ __forceinline__ unsigned long long globaltimer_ns() {

@@ -165,6 +165,12 @@ typedef struct {
 BNB_B200_API void cgemm_4bit_inference_nested_push_fp16(int m, int n, int k, void *A, unsigned char *B, unsigned char *qabsmax, float *absmax2, float *code2, float offset, float *datatype, void *out, int lda, int ldb, int ldc, int blocksize, int blocksize2, void **peer_outs, int npeers, const bnb_gemv_sync_t *sync);
 BNB_B200_API void cgemm_4bit_inference_nested_push_bf16(int m, int n, int k, void *A, unsigned char *B, unsigned char *qabsmax, float *absmax2, float *code2, float offset, float *datatype, void *out, int lda, int ldb, int ldc, int blocksize, int blocksize2, void **peer_outs, int npeers, const bnb_gemv_sync_t *sync);
 BNB_B200_API void cbnb_epoch_bump(unsigned int *epoch);
+/* Cross-GPU barrier of an N-sharded stack as one link of the programmatic-dependent-launch chain (stream-ordered,
+ * graph-capturable): waits for the previous kernel of the stream, then publishes ++*counter into every peer's slot
+ * (sig_peer: HOST array of npeers peer-mapped addresses) and waits until each of the npeers slots of sig_local holds
+ * at least that value.  counter: device int, zero-initialised, private to the caller; every rank must call it the
+ * same number of times.  The kernels after it may rely on all peers' earlier stores into symmetric memory. */
+BNB_B200_API void cbnb_peer_barrier(unsigned int *counter, const unsigned int *sig_local, unsigned int **sig_peer, int npeers);
 
 /* batch > 1 fused 4-bit GEMM (replaces dequantize_4bit + F.linear, autograd/_functions.py:490-518):
  * out[b, j] = sum_k A[b,k] * T(code[q(j,k)] * absmax[(j*K+k)/blocksize]) (+ bias[j]); A: [batch, K] T row-major,

@@ -69,14 +69,20 @@ mpeers = PeerOutputBuffers([N for (N, _) in mshapes], torch.bfloat16, dev)
 mpeers.buf.zero_()
 dist.barrier()
 torch.cuda.synchronize()
-sharded_gemv_push_multi(xm, [s[0] for s in mshards], [s[1] for s in mshards], mpeers, [0, 1, 2])
-mpeers.barrier()
-torch.cuda.synchronize()
-for i, (q, st) in enumerate(mfull):
-    ref = F.gemv_4bit(xm, q.t(), state=st)
-    if not torch.equal(ref.view(torch.int16), mpeers.full(i).view(torch.int16)):
-        ok = False
-        print(f"rank {rank} multi-launch shape {mshapes[i]}: MISMATCH", flush=True)
+for it in range(12):
+    if it == 2:
+        mpeers.enable_fast_barrier()      # from here on: cbnb_peer_barrier (a link of the PDL chain) instead of torch's
+    xi = (xm * (1.0 + 0.25 * it)).bfloat16()
+    sharded_gemv_push_multi(xi, [s[0] for s in mshards], [s[1] for s in mshards], mpeers, [0, 1, 2])
+    mpeers.barrier()
+    got = [mpeers.full(i).clone() for i in range(3)]    # stream-ordered after the barrier: every peer's slice is in
+    mpeers.barrier()                                     # nobody overwrites before everybody has read
+    torch.cuda.synchronize()
+    for i, (q, st) in enumerate(mfull):
+        ref = F.gemv_4bit(xi, q.t(), state=st)
+        if not torch.equal(ref.view(torch.int16), got[i].view(torch.int16)):
+            ok = False
+            print(f"rank {rank} multi-launch iter {it} shape {mshapes[i]}: MISMATCH", flush=True)
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
