@@ -877,7 +877,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
 
 #undef BNB_MSEL
 // ------------------------------------------------------------------------------------------------
-// TMA-staged block-column kernel (the production path for batch 1).
+// TMA-staged block-column kernel (experiment, BNB_B200_GEMV_CFG=3x: measured equal to the register ring).
 //
 // Same arithmetic as k_gemv4_bc, different data movement.  Global loads issued by the compute warps share the
 // LSU / L1TEX pipe with the LUT lookups, and that pipe -- not HBM, not issue slots -- is what bounds this kernel
