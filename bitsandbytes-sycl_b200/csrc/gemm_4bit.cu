@@ -14,7 +14,7 @@
 //               register file, holds the bytes in flight towards HBM (up to 64 KB per CTA) -- and the activation
 //               tile (one 128-byte-swizzled box per stage) into the operand ring
 //   warp 1      TMEM owner + single-thread tcgen05.mma issuer; tcgen05.commit frees an operand stage
-//   warps 2-5   dequant producers: thread r owns weight row r of the tile -- two LDS.128 of packed bytes per stage,
+//   warps 2-17  dequant producers (four groups of four warps, group g takes stages kb % 4 == g): thread r owns weight row r of the tile -- two LDS.128 of packed bytes per stage,
 //               16-entry fp32 code table in shared memory (16 words in 16 banks: conflict-free for any data),
 //               64 FMUL, cvt.rn.{bf16x2,f16x2}.f32, eight swizzled STS.128, fence.proxy.async, mbarrier arrive;
 //               after the main loop the same warps run the epilogue (tcgen05.ld -> +bias -> T -> global, or fp32
@@ -35,7 +35,7 @@ namespace bnb {
 namespace g4 {
 constexpr int TM = 128;            // weight rows per tile (UMMA M)
 constexpr int TK = 64;             // K elements per stage (128 bytes of T: one SWIZZLE_128B row)
-constexpr int kDqWarps = 8;         // dequant warps: groups of 4 (one thread per weight row), group g takes stages kb % G == g
+constexpr int kDqWarps = 16;        // dequant warps: groups of 4 (one thread per weight row), group g takes stages kb % G == g
 constexpr int kThreads = 64 + kDqWarps * 32;
 constexpr int kStageA = TM * 128;  // 16 KB
 constexpr int kMaxNB = 256;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gemm4_tcgen05(const __grid_cons
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(tc::smem_u32(emptyW + wslot));
       wslot += G;
-      if (wslot >= a.wslots) { wslot -= a.wslots; wphase ^= 1u; }
+      while (wslot >= a.wslots) { wslot -= a.wslots; wphase ^= 1u; }
 
       tc::mbar_wait(tc::smem_u32(empty + stage), phase ^ 1);
       const uint32_t dst = smem_s + stage * stage_bytes + r * 128;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gemm4_tcgen05(const __grid_cons
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(tc::smem_u32(fullA + stage));
       stage += G;
-      if (stage >= a.stages) { stage -= a.stages; phase ^= 1u; }
+      while (stage >= a.stages) { stage -= a.stages; phase ^= 1u; }
     }
 
     // ---- epilogue: TMEM lane quarter warp % 4 (two warps per quarter, alternating 32-column groups)
@@ -301,13 +301,15 @@ int gemm_4bit(int batch, int N, int K, const T *A, const unsigned char *B, const
   a.NB = (batch + 15) / 16 * 16;
   a.B = B; a.absmax = absmax; a.code = datatype; a.bias = bias; a.out = out;
   const int stage_bytes = kStageA + a.NB * 128;
-  const int budget = (a.NB <= 64 ? 110 : 220) * 1024;     // two CTAs per SM while the activation tile is small
-  a.stages = 3;
-  a.wslots = (budget - 2048 - a.stages * stage_bytes) / kStageW;
+  a.stages = kDqWarps / 4;                                 // one operand stage per dequant group (the groups' ring
+                                                           // arithmetic needs stages >= groups)
+  bool two_cta = a.NB <= 64;                               // two CTAs per SM while the activation tile is small
+  a.wslots = ((two_cta ? 110 : 220) * 1024 - 2048 - a.stages * stage_bytes) / kStageW;
+  if (two_cta && a.wslots < a.stages + 1) { two_cta = false; a.wslots = (220 * 1024 - 2048 - a.stages * stage_bytes) / kStageW; }
   if (a.wslots > kMaxWSlots) a.wslots = kMaxWSlots;
   if (a.wslots < a.stages + 1) return 1;
   const int tiles = (N + TM - 1) / TM;
-  const int target = num_sms[dev] * (a.NB <= 64 ? 2 : 1);
+  const int target = num_sms[dev] * (two_cta ? 2 : 1);
   int splits = target / tiles;
   const int kblocks = K / TK;
   if (splits > kblocks / 8) splits = kblocks / 8;          // at least 8 stages of work per CTA
