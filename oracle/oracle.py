@@ -269,6 +269,43 @@ def mm_dequant(C: np.ndarray, row_stats: np.ndarray, col_stats: np.ndarray, rows
     return out.view(np.float16)
 
 
+# ------------------------------------------------------------------------------------ a12 (orchestration)
+def llm_int8_forward(A_f16: np.ndarray, CB: np.ndarray, SCB: np.ndarray, bias_f16: Optional[np.ndarray],
+                     threshold: float):
+    """CPU restatement of MatMul8bitLt.forward with has_fp16_weights=False (reference
+    python_src_quants/autograd/_functions.py:292-434), composed from the per-kernel restatements above:
+      :340      CA, CAt, SCA, SCAt, coo = double_quant(A, threshold)                  -> get_col_row_stats + double_rowcol_quant
+      :369-372  idx = unique(coo.colidx)                                               (outlier feature columns)
+      :381      subB = (extract_outliers(CxB)[..idx] * SCB.view(-1,1) / 127).t().to(fp16)
+      :382-384  CA[:, idx] = 0 ; subA = A[:, idx]
+      :404-414  out32 = igemmlt(CA, CB) ; output = mm_dequant(out32, SCA, SCB, bias)
+      :431      output += matmul(subA, subB)       (fp16 operands, fp32 accumulation, fp16 result, fp16 add)
+    Returns (y float16 [m, n], CA int8 [m, k] with outlier columns zeroed, SCA float32 [m], idx int32 ascending)."""
+    A = np.ascontiguousarray(A_f16, np.float16)
+    m, k = A.shape
+    n = CB.shape[0]
+    row_stats, col_stats, nnz = get_col_row_stats(A, threshold)
+    if threshold > 0.0:
+        ptr = np.cumsum(nnz, dtype=np.int64).astype(np.int32)      # functional.py:2432
+        CA, _, _, colidx, _ = double_rowcol_quant(A, row_stats, col_stats, ptr, threshold)
+        idx = np.unique(colidx).astype(np.int32) if colidx is not None and colidx.size else np.zeros(0, np.int32)
+    else:
+        CA, _, _, _, _ = double_rowcol_quant(A, row_stats, col_stats)
+        idx = np.zeros(0, np.int32)
+    CA = CA.copy()
+    if idx.size:
+        CA[:, idx] = 0
+    acc = igemm_rowmajor(CA, CB)
+    y = mm_dequant(acc, row_stats, np.ascontiguousarray(SCB, np.float32), m, n, bias_f16, col32=False)
+    if idx.size:
+        subA = A[:, idx].astype(np.float32)
+        # fp32 product then one rounding to fp16, like the device expression (outliers * SCB / 127).to(fp16)
+        subB = ((CB[:, idx].astype(np.float32) * np.asarray(SCB, np.float32)[:, None]) / np.float32(127.0)).astype(np.float16)
+        side = (subA @ subB.astype(np.float32).T).astype(np.float16)      # fp32 accumulation, fp16 result
+        y = (y.astype(np.float32) + side.astype(np.float32)).astype(np.float16)
+    return y, CA, row_stats, idx
+
+
 def extract_outliers(A_fmt: np.ndarray, idx: np.ndarray, rows: int, cols: int, fmt: str) -> np.ndarray:
     idx = np.ascontiguousarray(idx, np.int32)
     out = np.zeros((rows, idx.size), np.int8)

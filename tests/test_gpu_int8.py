@@ -354,3 +354,36 @@ def test_linear8bitlt_state_dict_roundtrip(F):
     with torch.no_grad():
         y1 = lin2(x)
     assert torch.equal(y0, y1)
+
+
+@pytest.mark.parametrize("n_outlier_cols", [0, 2, 5])
+def test_int8_linear_fused_vs_oracle_orchestration(F, n_outlier_cols):
+    """The fused forward against the ORACLE's restatement of the reference orchestration (oracle.llm_int8_forward,
+    _functions.py:292-434): quantised activations, row statistics and outlier columns bit-exact; fp16 output within
+    2 ulp of max(|y|, |outlier term|) (only the fp32 summation order of the <= 8-term outlier product differs) and
+    bit-identical without outliers."""
+    torch.manual_seed(40 + n_outlier_cols)
+    m, k, n = 96, 512, 256
+    A = torch.randn(m, k).half()
+    cols = sorted(torch.randperm(k)[:n_outlier_cols].tolist())
+    for c in cols:
+        A[torch.randperm(m)[: m // 5], c] = 7.0 if c % 2 else -9.0
+    W = (torch.randn(n, k) * 0.05).half()
+    CB, _, SCB, _, _ = F.double_quant(W.cuda())
+    bias = torch.randn(n).half()
+    y, CA, SCA, idx, count = F.int8_linear_fused(A.cuda(), CB, SCB, bias=bias.cuda(), threshold=6.0, return_quantized=True)
+    torch.cuda.synchronize()
+    y_o, CA_o, SCA_o, idx_o = orc.llm_int8_forward(A.numpy(), CB.cpu().numpy(), SCB.cpu().numpy(), bias.numpy(), 6.0)
+    assert int(count.item()) == n_outlier_cols and idx[:n_outlier_cols].cpu().tolist() == idx_o.tolist() == cols
+    assert np.array_equal(CA.cpu().numpy(), CA_o)
+    assert np.array_equal(SCA.cpu().numpy().view(np.uint32), SCA_o.view(np.uint32))
+    yk = y.cpu().numpy()
+    if n_outlier_cols == 0:
+        assert np.array_equal(yk.view(np.uint16), y_o.view(np.uint16))
+    else:
+        subB = ((CB.cpu().numpy()[:, cols].astype(np.float32) * SCB.cpu().numpy()[:, None]) / np.float32(127.0)).astype(np.float16)
+        U = np.abs(A.numpy()[:, cols].astype(np.float32) @ subB.astype(np.float32).T)
+        ulp = np.maximum(np.maximum(np.abs(y_o.astype(np.float32)), U), 2.0 ** -14) * 2.0 ** -10
+        d = np.abs(yk.astype(np.float32) - y_o.astype(np.float32))
+        assert (d <= 2.01 * ulp).all(), float((d / ulp).max())
+        assert (d > 0).mean() < 0.02

@@ -256,3 +256,26 @@ def test_gemv_chains_close_to_exact():
         assert rel < tol, (mode, rel)
     y32 = orc.gemv_4bit(x.float().numpy(), "fp32", q, am, code, N, K, 64, 0)
     assert np.linalg.norm(y32 - exact) / np.linalg.norm(exact) < 1e-5
+
+
+def test_llm_int8_forward_restatement_tracks_the_fp32_product():
+    """oracle.llm_int8_forward (reference _functions.py:292-434 composed from the kernel restatements): outlier columns
+    are found, zeroed in CA and carried in 16 bit; the result tracks the fp32 product within int8 quantisation noise."""
+    rng = np.random.default_rng(3)
+    m, k, n = 48, 256, 64
+    A = rng.standard_normal((m, k)).astype(np.float16)
+    A[:, 17] = 8.0
+    A[5, 100] = -7.5
+    W = (rng.standard_normal((n, k)) * 0.05).astype(np.float16)
+    rs, cs, _ = orc.get_col_row_stats(W.T.copy().T, 0.0)        # row stats of W = SCB
+    CB, _, _, _, _ = orc.double_rowcol_quant(W, rs, cs)
+    bias = (rng.standard_normal(n) * 0.1).astype(np.float16)
+    y, CA, SCA, idx = orc.llm_int8_forward(A, CB, rs, bias, 6.0)
+    assert idx.tolist() == [17, 100]
+    assert not CA[:, 17].any() and not CA[:, 100].any()
+    ref = A.astype(np.float32) @ W.astype(np.float32).T + bias.astype(np.float32)
+    err = np.linalg.norm(y.astype(np.float32) - ref) / np.linalg.norm(ref)
+    assert err < 0.02, err
+    # threshold 0: no decomposition, plain int8 path
+    y0, CA0, _, idx0 = orc.llm_int8_forward(A, CB, rs, bias, 0.0)
+    assert idx0.size == 0 and CA0[:, 17].any()
