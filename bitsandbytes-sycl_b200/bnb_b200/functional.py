@@ -603,7 +603,14 @@ def gemm_4bit(A: Tensor, B: Tensor, state: QuantState, bias: Optional[Tensor] = 
     N, K = state.shape
     A2 = A.reshape(-1, A.shape[-1]).contiguous()
     batch = A2.shape[0]
-    absmax = _denest(state) if state.nested else state.absmax
+    if state.nested:
+        # the de-nested fp32 absmax (two launches, reference :1346-1350) is a constant of the frozen weight: computed
+        # once and kept with the state (+ 1/16 byte per weight) instead of once per forward
+        absmax = getattr(state, "_absmax_f32", None)
+        if absmax is None or absmax.device != A.device:
+            absmax = state._absmax_f32 = _denest(state)
+    else:
+        absmax = state.absmax
     if out is None:
         out = torch.empty((batch, N), dtype=A.dtype, device=A.device)
     code = state.code.to(A.device)
