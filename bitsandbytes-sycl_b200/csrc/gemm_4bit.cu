@@ -327,11 +327,11 @@ int gemm_4bit(int batch, int N, int K, const T *A, const unsigned char *B, const
   if (!make_tmap_2d(&tmX, A, 2, (uint64_t)batch, (uint64_t)K, (uint32_t)a.NB, TK, true, std::is_same<T, __nv_bfloat16>::value)) return 2;
   if (!make_tmap_2d(&tmW, B, 1, (uint64_t)N, (uint64_t)(K / 2), TM, TK / 2, false, false, false)) return 2;
   const size_t smem = (size_t)a.stages * stage_bytes + (size_t)a.wslots * kStageW + 1024 /*align*/ + 1024 /*barriers, code*/;
-  static bool attr_set[2] = {false, false};
+  static bool attr_set[2][64] = {{false}};      // per element type AND per device
   const int ti = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
-  if (!attr_set[ti]) {
+  if (!attr_set[ti][dev]) {
     latch_error(cudaFuncSetAttribute(k_gemm4_tcgen05<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024), "gemm_4bit smem attr");
-    attr_set[ti] = true;
+    attr_set[ti][dev] = true;
   }
   k_gemm4_tcgen05<T><<<dim3(tiles, a.splits), kThreads, smem, st>>>(tmX, tmW, a);
   check_launch("gemm_4bit (tcgen05)");

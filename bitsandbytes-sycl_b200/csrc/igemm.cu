@@ -377,14 +377,14 @@ static int igemm_rowmajor(const signed char *A, const signed char *B, const Igem
     CUtensorMap tmA, tmB;
     if (!make_tmap_2d(&tmA, A, 1, (uint64_t)a.M, (uint64_t)a.K, BM, BK, false, false)) return 2;
     if (!make_tmap_2d(&tmB, B, 1, (uint64_t)a.N, (uint64_t)a.K, BN, BK, false, false)) return 2;
-    static bool attr_set = false;
-    if (!attr_set) {
-      latch_error(cudaFuncSetAttribute(k_igemm_tcgen05<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIgemmSmem), "igemm smem attr");
-      attr_set = true;
-    }
-    const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
     int sms = kNumSMs, dev = 0;
     cudaGetDevice(&dev);
+    static bool attr_set[64] = {false};          // the attribute is per device: one process may drive several GPUs
+    if (!attr_set[dev & 63]) {
+      latch_error(cudaFuncSetAttribute(k_igemm_tcgen05<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIgemmSmem), "igemm smem attr");
+      attr_set[dev & 63] = true;
+    }
+    const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = tiles < sms ? tiles : sms;
     k_igemm_tcgen05<EPI><<<grid, kIgemmThreads, kIgemmSmem, st>>>(tmA, tmB, a);
