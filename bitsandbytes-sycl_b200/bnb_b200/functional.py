@@ -908,7 +908,7 @@ def int8_linear_fused(A: Tensor, CB: Tensor, SCB: Tensor, bias: Optional[Tensor]
     if ws is None:
         dev = A.device
         ws = dict(CA=torch.empty((m, k), dtype=torch.int8, device=dev), SCA=torch.empty(m, dtype=torch.float32, device=dev),
-                  colflag=torch.empty(k, dtype=torch.uint8, device=dev), pos=torch.empty(k, dtype=torch.int16, device=dev),
+                  colflag=torch.zeros(k, dtype=torch.uint8, device=dev), pos=torch.empty(k, dtype=torch.int16, device=dev),
                   idx=torch.zeros(max(k, 16), dtype=torch.int32, device=dev), count=torch.zeros(1, dtype=torch.int32, device=dev),
                   subA=torch.empty((m, 16), dtype=torch.float16, device=dev), subB=torch.empty((n, 16), dtype=torch.float16, device=dev))
         if len(_INT8_WS) > 8:

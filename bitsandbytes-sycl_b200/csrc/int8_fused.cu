@@ -22,6 +22,23 @@ namespace bnb {
 constexpr int kMaxOutliers = 16;   // leading dimension of subA / subB
 constexpr int kEpiOutliers = 8;    // outlier columns folded into the GEMM epilogue; the rest go through k_i8_outlier_tail
 
+// every kernel of the fused forward is a link of a programmatic-dependent-launch chain: it lets its successor's
+// CTAs be scheduled at once and waits for its predecessor before it touches memory
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = 0; lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr; lc.numAttrs = 1;
+  latch_error(cudaLaunchKernelEx(&lc, kernel, static_cast<KArgs>(args)...), "int8 fused launch");
+}
+
 __device__ __forceinline__ int quant_s8_(float x, float scale) {
   int q = __float2int_rn(__fmul_rn(x, scale));
   return max(-128, min(127, q));
@@ -30,6 +47,7 @@ __device__ __forceinline__ int quant_s8_(float x, float scale) {
 // one warp per row; 16 bytes per lane per step
 __global__ void __launch_bounds__(256) k_i8_rowstats_flags(const __half *__restrict__ A, float *__restrict__ rowStats,
                                                            unsigned char *__restrict__ colflag, float thr, int rows, int cols) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -51,8 +69,9 @@ __global__ void __launch_bounds__(256) k_i8_rowstats_flags(const __half *__restr
 }
 
 // single CTA: ordered compaction of the column flags
-__global__ void __launch_bounds__(1024) k_i8_compact(const unsigned char *__restrict__ colflag, int *__restrict__ idx,
+__global__ void __launch_bounds__(1024) k_i8_compact(unsigned char *__restrict__ colflag, int *__restrict__ idx,
                                                      short *__restrict__ pos, int *__restrict__ count, int cols, int idx_cap) {
+  pdl_enter();
   __shared__ int s_warp[32];
   __shared__ int s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -61,6 +80,7 @@ __global__ void __launch_bounds__(1024) k_i8_compact(const unsigned char *__rest
   for (int c0 = 0; c0 < cols; c0 += 1024) {
     const int c = c0 + tid;
     const int f = (c < cols && colflag[c]) ? 1 : 0;
+    if (f) colflag[c] = 0;                 // self-cleaning: the flags are all zero again for the next forward
     const unsigned m = __ballot_sync(0xffffffffu, f);
     const int in_warp = __popc(m & ((1u << lane) - 1));
     if (lane == 0) s_warp[warp] = __popc(m);
@@ -82,6 +102,7 @@ __global__ void __launch_bounds__(1024) k_i8_compact(const unsigned char *__rest
 __global__ void __launch_bounds__(256) k_i8_quant_rows(const __half *__restrict__ A, const float *__restrict__ rowStats,
                                                        const short *__restrict__ pos, signed char *__restrict__ CA,
                                                        __half *__restrict__ subA, int rows, int cols) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -111,6 +132,7 @@ template <int NV>
 __global__ void __launch_bounds__(256) k_i8_row_onepass(const __half *__restrict__ A, float *__restrict__ rowStats,
                                                         unsigned char *__restrict__ colflag, signed char *__restrict__ CA,
                                                         float thr, int rows, int cols) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -153,19 +175,26 @@ __global__ void __launch_bounds__(256) k_i8_row_onepass(const __half *__restrict
 __global__ void __launch_bounds__(256) k_i8_fix_outliers(const __half *__restrict__ A, signed char *__restrict__ CA,
                                                          __half *__restrict__ subA, const int *__restrict__ idx,
                                                          const int *__restrict__ count, int rows, int cols, int idx_cap) {
+  pdl_enter();
   const int n = min(*count, idx_cap);
-  if (n <= 0) return;
-  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < (long)rows * n; i += (long)gridDim.x * 256) {
-    const int r = (int)(i / n), o = (int)(i % n);
-    const int c = idx[o];
-    CA[(size_t)r * cols + c] = 0;
-    if (o < kMaxOutliers) subA[(size_t)r * kMaxOutliers + o] = A[(size_t)r * cols + c];
+  if (n <= 0) return;                       // no outlier column: the GEMM epilogue does not read subA
+  const int w = max(n, kMaxOutliers);       // subA is written in full (zeros past the last outlier column): no memset
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < (long)rows * w; i += (long)gridDim.x * 256) {
+    const int r = (int)(i / w), o = (int)(i % w);
+    if (o < n) {
+      const int c = idx[o];
+      CA[(size_t)r * cols + c] = 0;
+      if (o < kMaxOutliers) subA[(size_t)r * kMaxOutliers + o] = A[(size_t)r * cols + c];
+    } else {
+      subA[(size_t)r * kMaxOutliers + o] = __float2half(0.f);
+    }
   }
 }
 
 __global__ void __launch_bounds__(256) k_i8_subB(const signed char *__restrict__ CB, const float *__restrict__ SCB,
                                                  const int *__restrict__ idx, const int *__restrict__ count,
                                                  __half *__restrict__ subB, int n, int k) {
+  pdl_enter();
   const int nout = min(*count, kMaxOutliers);
   const long i = (long)blockIdx.x * 256 + threadIdx.x;
   if (i >= (long)n * kMaxOutliers) return;
@@ -180,6 +209,7 @@ __global__ void __launch_bounds__(256) k_i8_outlier_tail(const __half *__restric
                                                          const float *__restrict__ SCB, const int *__restrict__ idx,
                                                          const int *__restrict__ count, __half *__restrict__ out, int m, int n,
                                                          int k, int idx_cap) {
+  pdl_enter();
   const int nout = min(*count, idx_cap);
   if (nout <= kEpiOutliers) return;
   for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < (long)m * n; i += (long)gridDim.x * 256) {
@@ -209,25 +239,26 @@ int int8_linear_fused(const __half *A, const signed char *CB, const float *SCB, 
       (reinterpret_cast<uintptr_t>(CA) % 16) != 0 || (reinterpret_cast<uintptr_t>(pos) % 16) != 0)
     return 1;
   cudaStream_t st = current_stream();
-  latch_error(cudaMemsetAsync(colflag, 0, (size_t)k, st), "int8 fused memset");
-  latch_error(cudaMemsetAsync(subA, 0, (size_t)m * kMaxOutliers * sizeof(__half), st), "int8 fused memset");
+  // colflag must be all zero on entry: the caller allocates it zeroed once, k_i8_compact clears what it consumed
+  const dim3 rows8((unsigned)ceil_div(m, 8)), b256(256);
   if (k <= 4096) {
     // one pass over A: the row stays in registers between the statistics and the quantisation
-    if (k <= 1024) k_i8_row_onepass<4><<<ceil_div(m, 8), 256, 0, st>>>(A, SCA, colflag, CA, thr, m, k);
-    else if (k <= 2048) k_i8_row_onepass<8><<<ceil_div(m, 8), 256, 0, st>>>(A, SCA, colflag, CA, thr, m, k);
-    else k_i8_row_onepass<16><<<ceil_div(m, 8), 256, 0, st>>>(A, SCA, colflag, CA, thr, m, k);
-    k_i8_compact<<<1, 1024, 0, st>>>(colflag, idx, pos, count, k, idx_cap);
-    k_i8_fix_outliers<<<kNumSMs, 256, 0, st>>>(A, CA, subA, idx, count, m, k, idx_cap);
+    if (k <= 1024) launch_pdl(k_i8_row_onepass<4>, rows8, b256, st, A, SCA, colflag, CA, thr, m, k);
+    else if (k <= 2048) launch_pdl(k_i8_row_onepass<8>, rows8, b256, st, A, SCA, colflag, CA, thr, m, k);
+    else launch_pdl(k_i8_row_onepass<16>, rows8, b256, st, A, SCA, colflag, CA, thr, m, k);
+    launch_pdl(k_i8_compact, dim3(1), dim3(1024), st, colflag, idx, pos, count, k, idx_cap);
+    launch_pdl(k_i8_fix_outliers, dim3(kNumSMs), b256, st, A, CA, subA, idx, count, m, k, idx_cap);
   } else {
-    k_i8_rowstats_flags<<<ceil_div(m, 8), 256, 0, st>>>(A, SCA, colflag, thr, m, k);
-    k_i8_compact<<<1, 1024, 0, st>>>(colflag, idx, pos, count, k, idx_cap);
-    k_i8_quant_rows<<<ceil_div(m, 8), 256, 0, st>>>(A, SCA, pos, CA, subA, m, k);
+    launch_pdl(k_i8_rowstats_flags, rows8, b256, st, A, SCA, colflag, thr, m, k);
+    launch_pdl(k_i8_compact, dim3(1), dim3(1024), st, colflag, idx, pos, count, k, idx_cap);
+    latch_error(cudaMemsetAsync(subA, 0, (size_t)m * kMaxOutliers * sizeof(__half), st), "int8 fused memset");
+    launch_pdl(k_i8_quant_rows, rows8, b256, st, A, SCA, pos, CA, subA, m, k);
   }
-  k_i8_subB<<<(unsigned)ceil_div_ll((long)n * kMaxOutliers, 256), 256, 0, st>>>(CB, SCB, idx, count, subB, n, k);
+  launch_pdl(k_i8_subB, dim3((unsigned)ceil_div_ll((long)n * kMaxOutliers, 256)), b256, st, CB, SCB, idx, count, subB, n, k);
   check_launch("int8 fused quantisation");
   const int rc = igemm_rowmajor_dequant_outliers_fp16(m, n, k, CA, CB, SCA, SCB, bias, out, subA, subB, count);
   if (rc != 0) return rc;
-  k_i8_outlier_tail<<<2 * kNumSMs, 256, 0, st>>>(A, CB, SCB, idx, count, out, m, n, k, idx_cap);
+  launch_pdl(k_i8_outlier_tail, dim3(2 * kNumSMs), b256, st, A, CB, SCB, idx, count, out, m, n, k, idx_cap);
   check_launch("int8 fused outlier tail");
   return 0;
 }

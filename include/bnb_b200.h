@@ -190,7 +190,7 @@ BNB_B200_API int cigemm_rowmajor_dequant_fp16(int m, int n, int k, const int8_t 
  * device-side compaction, row quantisation with the outlier columns zeroed, int8 tcgen05 GEMM with the mm_dequant
  * epilogue and the 16-bit outlier product folded into it.  A fp16 [m,k]; CB int8 [n,k] row-major; SCB fp32[n]; bias
  * fp16[n] or NULL; out fp16 [m,n].  Caller-owned device workspace: CA int8 [m,k], SCA fp32[m] (both are outputs too:
- * the quantised activations and their row statistics), colflag u8[k], pos i16[k] (16-byte aligned), idx i32[idx_cap
+ * the quantised activations and their row statistics), colflag u8[k] (ALL ZERO on entry; left all zero on return), pos i16[k] (16-byte aligned), idx i32[idx_cap
  * >= 16] (ascending outlier columns), count i32[1], subA fp16 [m,16], subB fp16 [n,16].  Returns 0 ok, 1 shape not
  * taken (caller runs the step-by-step path), 2 error. */
 BNB_B200_API int cint8_linear_fp16(void *A, const int8_t *CB, float *SCB, void *bias, void *out, float threshold, int m, int n, int k, int8_t *CA, float *SCA, unsigned char *colflag, short *pos, int *idx, int idx_cap, int *count, void *subA, void *subB);
