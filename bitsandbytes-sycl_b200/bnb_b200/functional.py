@@ -603,6 +603,26 @@ def gemm_4bit(A: Tensor, B: Tensor, state: QuantState, bias: Optional[Tensor] = 
     N, K = state.shape
     A2 = A.reshape(-1, A.shape[-1]).contiguous()
     batch = A2.shape[0]
+    if (2 <= batch <= 8 and bias is None and state.nested and FUSED_NESTED_GEMV and K % 64 == 0 and N % 16 == 0
+            and state.blocksize % 64 == 0 and A2.shape[1] == K and B.dtype == torch.uint8):
+        # batch 2..8: the batch rides in the MMA's n dimension of the LUT + mma.sync GEMV kernels (nested absmax read
+        # directly, fp32 absmax applied to fp32 partial sums): ~1.8x faster than the tcgen05 kernel at these sizes
+        # (18.5 vs 34 us on 14336x4096), and no de-nested absmax copy.
+        if out is None:
+            out = torch.empty((batch, N), dtype=A.dtype, device=A.device)
+        s2 = state.state2
+        offset = getattr(state, "_offset_host", None)
+        if offset is None:
+            offset = state._offset_host = float(state.offset)
+        code = state.code.to(A.device)
+        prev = pre_call(A.device)
+        is_on_gpu([A2, B, state.absmax, s2.absmax, s2.code, code, out])
+        getattr(lib, f"cgemm_4bit_inference_nested_{_SUFFIX[A.dtype]}")(
+            ct.c_int32(N), ct.c_int32(batch), ct.c_int32(K), get_ptr(A2), get_ptr(B), get_ptr(state.absmax),
+            get_ptr(s2.absmax), get_ptr(s2.code), ct.c_float(offset), get_ptr(code), get_ptr(out),
+            ct.c_int32(N), ct.c_int32((K + 1) // 2), ct.c_int32(N), ct.c_int32(state.blocksize), ct.c_int32(s2.blocksize))
+        post_call(prev)
+        return out.reshape(*A.shape[:-1], N)
     if state.nested:
         # the de-nested fp32 absmax (two launches, reference :1346-1350) is a constant of the frozen weight: computed
         # once and kept with the state (+ 1/16 byte per weight) instead of once per forward

@@ -138,3 +138,31 @@ def test_matmul4bit_backward(F):
     assert float((x.grad.float() - gA).norm() / gA.norm()) < 5e-3
     gb = g.float().sum(0)
     assert float((bias.grad.float() - gb).norm() / gb.norm()) < 1e-2
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("batch,N,K,with_bias", [(2, 4096, 4096, False), (5, 256, 1024, False), (8, 1024, 11008, False),
+                                                 (5, 130, 1024, True)])   # last one: bias / ragged N -> stays on the tcgen05 kernel
+def test_small_batch_rides_the_gemv_kernels(F, batch, N, K, dtype, with_bias):
+    """batch 2..8 with a nested state: the batch is the MMA n dimension of the GEMV kernels (cgemm_4bit_inference_nested_*
+    with n = batch).  Gate: rel-L2 vs the fp64 product with the EXACT (fp32 code x fp32 absmax) weights, the GEMV
+    tolerances of test_gpu_gemv (2.5e-3 bf16 / 6e-4 fp16), per batch row."""
+    import copy
+    torch.manual_seed(batch * 100 + N)
+    W = (torch.randn(N, K) * 0.02).to(DT[dtype]).cuda()
+    x = torch.randn(batch, K).to(DT[dtype]).cuda()
+    bias = torch.randn(N).to(DT[dtype]).cuda() if with_bias else None
+    q, st = F.quantize_4bit(W, blocksize=64, compress_statistics=True, quant_type="nf4")
+    y = F.gemm_4bit(x, q, st, bias=bias)
+    assert y is not None and y.shape == (batch, N) and y.dtype == DT[dtype]
+    st32 = copy.copy(st)
+    st32.dtype = torch.float32
+    ref = x.double() @ F.dequantize_4bit(q, st32).double().t()
+    if bias is not None:
+        ref = ref + bias.double()
+    tol = 2.5e-3 if dtype == "bf16" else 6e-4
+    if with_bias:
+        tol *= 1.6        # tcgen05 route: the operand is rounded to T first (reference arithmetic), see test_gemm_4bit_vs_fp64
+    for b in range(batch):
+        err = float((y[b].double() - ref[b]).norm() / ref[b].norm())
+        assert err <= tol, (b, err)
