@@ -23,7 +23,7 @@ FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     # bit-exactness: never contract a*b+c behind our back; IEEE div/sqrt; keep denormals
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-]
+] + os.environ.get("BNB_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _digest(paths):

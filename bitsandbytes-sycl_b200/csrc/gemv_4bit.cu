@@ -18,7 +18,9 @@
 //     double-buffering (8 x 64-bit loads per lane in flight per chunk), deterministic smem reduction.
 // The MMA's n dimension carries the batch (1..8 activations rows) at no extra cost.
 #include <stdlib.h>
+#include <mutex>
 #include <type_traits>
+#include <unordered_map>
 
 #include "codebooks.cuh"
 #include "common.cuh"
@@ -98,7 +100,23 @@ struct GemvArgs {
   const unsigned int *epoch;
   unsigned int *cta_counter;    // per-GPU scratch, zero at rest
   int gidx, ngroups, do_signal, do_wait;
+  // next-weight hint (history prefetcher, see gemv_next_hint below): the packed weight and nested absmax the NEXT
+  // GEMV of this thread is expected to stream; every CTA pulls its share into L2 while this kernel is LSU-bound
+  const unsigned char *pf_ptr[2];
+  unsigned int pf_bytes[2];
 };
+
+// one warp pulls slice `part` of `nparts` of [p, p + bytes) into L2: bulk prefetches of <= 8 KB, no data returns to the SM
+__device__ __forceinline__ void l2_prefetch_slice(const unsigned char *p, unsigned int bytes, unsigned int part, unsigned int nparts, int lane) {
+  const unsigned int units = (bytes + 255u) >> 8;
+  const unsigned int b0 = (unsigned int)((unsigned long long)units * part / nparts) << 8;
+  unsigned int b1 = (unsigned int)((unsigned long long)units * (part + 1) / nparts) << 8;
+  if (b1 > (bytes & ~15u)) b1 = bytes & ~15u;
+  for (unsigned int off = b0 + (unsigned int)lane * 8192u; off < b1; off += 32u * 8192u) {
+    const unsigned int len = min(8192u, b1 - off);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + off), "r"(len) : "memory");
+  }
+}
 
 // host-side mirror of bnb_gemv_sync_t (include/bnb_b200.h)
 struct GemvSync {
@@ -694,6 +712,11 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
     }
     advance(ltl, lc);
   }
+  if (warp == WARPS - 1) {
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+      if (a.pf_bytes[u]) l2_prefetch_slice(a.pf_ptr[u], a.pf_bytes[u], blockIdx.x, gridDim.x, lane);
+  }
 
   // ---- prologue (overlaps the first weight loads): tables and partial-sum slots; everything here reads only
   // constants (code, code2), so it may run before the previous kernel of the stream has finished
@@ -876,6 +899,8 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
 }
 
 #undef BNB_MSEL
+#include "gemv_v2.cuh"
+#include "gemv_t.cuh"
 // ------------------------------------------------------------------------------------------------
 // TMA-staged block-column kernel (experiment, BNB_B200_GEMV_CFG=3x: measured equal to the register ring).
 //
@@ -1534,6 +1559,12 @@ static void launch_mma_inst(const GemvArgs &a) {
       return;
     }
   }
+  static int impl_v2 = -1;
+  if (impl_v2 < 0) { const char *e = getenv("BNB_B200_GEMV_IMPL"); impl_v2 = (e && e[0] == '2') ? 1 : 0; }
+  static int impl_t = -1;
+  if (impl_t < 0) { const char *e = getenv("BNB_B200_GEMV_IMPL"); impl_t = (e && e[0] == 'T') ? 1 : 0; }
+  if (VEC4 && impl_t && a.batch == 1 && !exp_mode && launch_t<T, NESTED, false>(a2, ceil_div(a.N, 16), num_sms[dev])) return;
+  if (VEC4 && impl_v2 && a.batch == 1 && !exp_mode && launch_v2<T, NESTED, false>(a2, ceil_div(a.N, 16), num_sms[dev])) return;
   if (VEC4 && impl_bc && a.batch == 1) {
     // block-column kernel, register ring.  Default: 8-warp CTAs, two per SM (<= 113 KB of shared memory and <= 128
     // registers each), so consecutive GEMVs of a stream overlap through programmatic dependent launch; 16-warp
@@ -1628,6 +1659,61 @@ void gemv_4bit(int m, int n, int k, const T *A, const unsigned char *B, const fl
   check_launch("gemv_4bit (generic)");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Next-weight prefetcher.  Token-by-token decoding calls the same weights in the same order over and over, and a
+// batch-1 GEMV is bound by the shared-memory lookup pipe, not by HBM: while GEMV i runs, HBM has
+// room to bring the weight of GEMV i+1 into the 126 MB L2.  The library remembers, per packed-weight pointer, which
+// weight was streamed next the last time (a one-entry Markov table) and passes it to the kernel as a HINT; every
+// CTA issues bulk L2 prefetches for its share.  A hint is advisory: a wrong one costs bandwidth, never
+// correctness; a hint whose range is not inside a live device allocation (cuMemGetAddressRange) is dropped.
+// BNB_B200_GEMV_NEXTPF=0 switches the prefetcher off; cbnb_gemv_set_next_weight() overrides the history.
+// ------------------------------------------------------------------------------------------------
+struct NextHint { const void *B; size_t bytes; const void *q; size_t qbytes; };
+static std::mutex g_pf_mu;
+static std::unordered_map<const void *, NextHint> g_pf_next;
+static thread_local const void *tl_prev_B = nullptr;
+static thread_local NextHint tl_forced_hint = {nullptr, 0, nullptr, 0};
+void gemv_set_next_weight(const void *B, size_t bytes, const void *q, size_t qbytes) { tl_forced_hint = NextHint{B, bytes, q, qbytes}; }
+
+static bool device_range_ok(const void *p, size_t bytes) {
+  typedef CUresult (*fn_t)(CUdeviceptr *, size_t *, CUdeviceptr);
+  static fn_t fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *q = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &q, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<fn_t>(q);
+  }
+  if (!fn || !p || !bytes) return false;
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (fn(&base, &size, (CUdeviceptr)(uintptr_t)p) != CUDA_SUCCESS) return false;
+  return (uintptr_t)p + bytes <= (uintptr_t)base + size;
+}
+
+static void next_hint(GemvArgs &a, const void *B, size_t bytes, const void *q, size_t qbytes) {
+  static int off = -1;
+  if (off < 0) { const char *e = getenv("BNB_B200_GEMV_NEXTPF"); off = (e && e[0] == '0') ? 1 : 0; }
+  if (off) return;
+  NextHint h{nullptr, 0, nullptr, 0};
+  if (tl_forced_hint.B) { h = tl_forced_hint; tl_forced_hint = NextHint{nullptr, 0, nullptr, 0}; }
+  {
+    std::lock_guard<std::mutex> lk(g_pf_mu);
+    if (!h.B) { auto it = g_pf_next.find(B); if (it != g_pf_next.end()) h = it->second; }
+    if (tl_prev_B && tl_prev_B != B) g_pf_next[tl_prev_B] = NextHint{B, bytes, q, qbytes};
+    if (g_pf_next.size() > 65536) g_pf_next.clear();
+  }
+  tl_prev_B = B;
+  if (h.B && h.B != B && h.bytes < (1ull << 31) && (reinterpret_cast<uintptr_t>(h.B) % 16) == 0 && device_range_ok(h.B, h.bytes)) {
+    a.pf_ptr[0] = static_cast<const unsigned char *>(h.B); a.pf_bytes[0] = (unsigned int)h.bytes;
+    if (h.q && h.qbytes < (1ull << 31) && (reinterpret_cast<uintptr_t>(h.q) % 16) == 0 && device_range_ok(h.q, h.qbytes)) {
+      a.pf_ptr[1] = static_cast<const unsigned char *>(h.q); a.pf_bytes[1] = (unsigned int)h.qbytes;
+    }
+  }
+}
+
 // host copies of code[16] / code2[256] for the NEXT nested GEMV of this thread (consumed by that call)
 static thread_local const float *tl_code_host = nullptr, *tl_code2_host = nullptr;
 void set_gemv_host_tables(const float *code16, const float *code2_256) { tl_code_host = code16; tl_code2_host = code2_256; }
@@ -1668,6 +1754,7 @@ void gemv_4bit_nested(int m, int n, int k, const T *A, const unsigned char *B, c
       for (int i = 0; i < npeers; i++) a.sig_peer[i] = sync->sig_peer[i];
     }
   }
+  if (n == 1) next_hint(a, B, (size_t)m * (size_t)(k / 2), qabsmax, (size_t)m * (size_t)(k / blocksize));
   launch_mma<T, true>(a, blocksize2);
 }
 
@@ -1714,6 +1801,14 @@ int gemv_4bit_nested_multi(int count, const int *ms, int k, const T *A, const un
   auto smem_need = [&](int warps, int grid) {
     return (size_t)65536 + kBcHead + (size_t)xblocks * kBcXPitch + (size_t)ceil_div(tiles, grid) * warps * 16 * sizeof(float);
   };
+  {
+    static int impl_v2 = -1;
+    if (impl_v2 < 0) { const char *e = getenv("BNB_B200_GEMV_IMPL"); impl_v2 = (e && e[0] == '2') ? 1 : 0; }
+    static int impl_t = -1;
+    if (impl_t < 0) { const char *e = getenv("BNB_B200_GEMV_IMPL"); impl_t = (e && e[0] == 'T') ? 1 : 0; }
+    if (impl_t && launch_t<T, true, true>(a, tiles, sms)) return 0;
+    if (impl_v2 && launch_v2<T, true, true>(a, tiles, sms)) return 0;
+  }
   int warps = 8, grid = tiles < sms * 2 ? tiles : sms * 2;
   if (smem_need(warps, grid) > (size_t)(113 * 1024)) { warps = 16; grid = tiles < sms ? tiles : sms; }
   const size_t need = smem_need(warps, grid);

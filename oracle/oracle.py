@@ -247,6 +247,19 @@ def igemmlt_32(A_col32: np.ndarray, B_fmt: np.ndarray, m: int, n: int, k: int, f
     return C
 
 
+def igemmlt_8(A_col32: np.ndarray, B_fmt: np.ndarray, m: int, n: int, k: int, fmtB: str,
+              row_scale: Optional[np.ndarray] = None) -> np.ndarray:
+    """int8-output igemmlt (reference op_gemm.cpp:604-638 -> pythonInterface.cpp:303-316 cigemmlt_<fmt>_8 /
+    _8_rowscale): the int32 accumulator is scaled in fp32 -- alpha = 1.0f, or the per-row vector row_scale[i]
+    (matmul_desc pointer_mode = alpha vector, :624-632) -- rounded to nearest-even and saturated to int8; C is col32.
+    The arithmetic lives in oneDNN / cublasLt (not in /root/reference): parity unpinned by the reference's tests;
+    this is the documented semantics of an int8 D with an fp32 scale."""
+    acc = untransform(igemmlt_32(A_col32, B_fmt, m, n, k, fmtB), "col32", m, n).astype(np.float32)
+    alpha = np.ones((m, 1), np.float32) if row_scale is None else np.asarray(row_scale, np.float32).reshape(m, 1)
+    q = np.clip(np.rint(acc * alpha), -128, 127).astype(np.int8)
+    return transform(q, "col32")
+
+
 def igemm_rowmajor(A: np.ndarray, B: np.ndarray) -> np.ndarray:
     A = np.ascontiguousarray(A, np.int8)
     B = np.ascontiguousarray(B, np.int8)

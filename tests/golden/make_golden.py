@@ -14,6 +14,10 @@ What it captures (nothing here is typed in by hand):
   * ref_cpu_blockwise.npz -- inputs and outputs of the reference's compiled sycl/cpu_ops.cpp
     (oracle/_ref/libref_cpu.so): quantize_cpu / dequantize_cpu on seeded data at blocksize 64 and 4096,
     including a ragged tail and a run of zeros.
+  * ref_device_trees.npz -- outputs of the reference's scalar DEVICE functions (dQuantizeNF4, dQuantizeFP4,
+    dQuantize<0>, dDequantizeNF4, dDequantizeFP4Tree; kernel_quant.cpp:519-837) whose bodies are cut out of the
+    reference source verbatim and compiled with g++ in a temporary directory, on ~260 k seeded inputs plus every
+    decision threshold +- 1 ulp.  Inputs are regenerated from the seed by the test (tree_inputs()).
 The fixtures travel to the GPU box; /root/reference does not.
 """
 import ast
@@ -127,8 +131,79 @@ def cpu_blockwise():
     print("cpu blockwise fixtures:", {k: v.shape for k, v in cases.items()})
 
 
+def tree_inputs():
+    """The inputs of ref_device_trees.npz, regenerated identically by tests/test_oracle.py: seeded values in and around
+    [-1, 1] plus, for every decision threshold of the three quantisers, the threshold itself and its two neighbours."""
+    tables = np.load(os.path.join(HERE, "ref_python_tables.npz"))
+    consts = json.load(open(os.path.join(HERE, "ref_kernel_constants.json")))
+    rng = np.random.RandomState(20241)
+    x = np.concatenate([rng.uniform(-1.05, 1.05, 200000), rng.randn(40000) * 0.3, rng.uniform(-0.01, 0.01, 20000)]).astype(np.float32)
+    code = tables["dynamic_map"].astype(np.float32)
+    thr = [np.float32(v) for v in consts["nf4_thresholds_ascending"]]
+    thr += [np.float32(v) for v in consts["fp4_quant_thresholds_tree_order"]] + [-np.float32(v) for v in consts["fp4_quant_thresholds_tree_order"]]
+    thr += list(code) + list(((code[1:].astype(np.float64) + code[:-1]) * 0.5).astype(np.float32))     # 8-bit pivots and midpoints
+    thr = np.array(thr, np.float32)
+    special = np.concatenate([thr, np.nextafter(thr, np.float32(2)), np.nextafter(thr, np.float32(-2)),
+                              np.array([0.0, -0.0, 1.0, -1.0, 1e-42, -3e-41, 1.5, -1.5, np.inf, -np.inf, np.nan], np.float32)])
+    return np.concatenate([x, special.astype(np.float32)]), code
+
+
+def device_trees():
+    """Reference-EXECUTED golden vectors for the scalar device functions: the bodies of dDequantizeFP4Tree, dQuantizeFP4,
+    dDequantizeNF4, dQuantizeNF4 and dQuantize<0> (kernel_quant.cpp:519-837, plain scalar C++) are cut out of the
+    reference source verbatim, compiled with g++ under /tmp (never written into this repo) and run on tree_inputs()."""
+    import ctypes as ct
+    import subprocess
+    import tempfile
+    src = open(os.path.join(REF, "sycl/sycl_code/kernel_quant.cpp")).read()
+    sigs = [r"float dDequantizeFP4Tree\(unsigned char val, float absmax\)", r"unsigned char dQuantizeFP4\(float x\)",
+            r"float dDequantizeNF4\(unsigned char val\)", r"unsigned char dQuantizeNF4\(float x\)",
+            r"template <int STOCHASTIC>\s*unsigned char dQuantize\(float\* smem_code, const float rand, float x\)"]
+    parts = []
+    for sg in sigs:
+        m = re.search(sg, src)
+        assert m, sg
+        parts.append(m.group(0) + "\n" + body_of(src, sg))
+    shim = ("#include <cmath>\nnamespace sycl { static inline float fabs(float v) { return std::fabs(v); } }\n" + "\n".join(parts) +
+            "\nextern \"C\" {\n"
+            "void run_nf4(const float* x, unsigned char* q, long n) { for (long i = 0; i < n; i++) q[i] = dQuantizeNF4(x[i]); }\n"
+            "void run_fp4(const float* x, unsigned char* q, long n) { for (long i = 0; i < n; i++) q[i] = dQuantizeFP4(x[i]); }\n"
+            "void run_q8(float* code, const float* x, unsigned char* q, long n) { for (long i = 0; i < n; i++) q[i] = dQuantize<0>(code, 0.0f, x[i]); }\n"
+            "void run_deq(float* nf4, float* fp4, float absmax) { for (int i = 0; i < 16; i++) { nf4[i] = dDequantizeNF4((unsigned char)i); fp4[i] = dDequantizeFP4Tree((unsigned char)i, absmax); } }\n"
+            "}\n")
+    with tempfile.TemporaryDirectory(prefix="bnb_ref_trees_") as td:
+        cpp, so = os.path.join(td, "trees.cpp"), os.path.join(td, "trees.so")
+        open(cpp, "w").write(shim)
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, cpp])
+        lib = ct.CDLL(so)
+        x, code = tree_inputs()
+        n = x.size
+        out = {}
+        fp = lambda a: a.ctypes.data_as(ct.c_void_p)
+        for name, fn in (("nf4", lib.run_nf4), ("fp4", lib.run_fp4)):
+            q = np.zeros(n, np.uint8)
+            fn(fp(x), fp(q), ct.c_long(n))
+            out["q_" + name] = q
+        q = np.zeros(n, np.uint8)
+        code_c = np.ascontiguousarray(code)
+        finite = np.isfinite(x)                           # the 8-bit search is only defined for finite inputs
+        xf = np.ascontiguousarray(x[finite])
+        qf = np.zeros(xf.size, np.uint8)
+        lib.run_q8(fp(code_c), fp(xf), fp(qf), ct.c_long(xf.size))
+        out["q_8bit_finite"] = qf
+        nf4 = np.zeros(16, np.float32)
+        fp4 = np.zeros(16, np.float32)
+        lib.run_deq(fp(nf4), fp(fp4), ct.c_float(0.73))
+        out["deq_nf4"], out["deq_fp4_absmax0p73"] = nf4, fp4
+    out["n_inputs"] = np.array([n], np.int64)
+    out["x_crc"] = np.array([int(np.bitwise_xor.reduce(x.view(np.uint32)))], np.int64)
+    np.savez_compressed(os.path.join(HERE, "ref_device_trees.npz"), **out)
+    print("device tree fixtures:", {k: (v.shape, v.dtype) for k, v in out.items()}, "bytes", os.path.getsize(os.path.join(HERE, "ref_device_trees.npz")))
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run this where /root/reference exists"
     python_tables()
     kernel_constants()
     cpu_blockwise()
+    device_trees()

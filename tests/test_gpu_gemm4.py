@@ -23,6 +23,11 @@ def F():
 def reference64(F, x, q, st, dtype, bias=None):
     """fp64 product with the dequantised weight rounded to T exactly like dequantize_4bit."""
     Wd = F.dequantize_4bit(q, st).to(DT[dtype])            # K2 kernel: bit-exact with the oracle (test_gpu_blockwise)
+    if Wd.numel() > (1 << 24):                             # config-4 sizes: the fp64 product itself runs on the device
+        y = x.double().cuda() @ Wd.double().t()
+        if bias is not None:
+            y = y + bias.double()[None, :]
+        return y.cpu().numpy()
     y = x.double().cpu().numpy() @ Wd.double().cpu().numpy().T
     if bias is not None:
         y = y + bias.double().cpu().numpy()[None, :]
@@ -37,6 +42,15 @@ CASES = [
     (32, 128, 8192, "bf16", True, 64, True),       # one row tile -> split-K + finalize
     (64, 4096, 14336, "bf16", True, 64, False),    # Llama-3-8B down projection: split-K
     (16, 1024, 4096, "fp16", False, 128, False),   # blocksize 128
+    # BASELINE config 4 (Llama-3-8B MLP), the shapes and batches the kernel numbers are quoted on
+    (16, 14336, 4096, "bf16", True, 64, False),
+    (32, 14336, 4096, "bf16", True, 64, True),
+    (128, 14336, 4096, "bf16", True, 64, False),
+    (256, 14336, 4096, "bf16", True, 64, True),
+    (16, 14336, 4096, "fp16", True, 64, True),
+    (256, 14336, 4096, "fp16", True, 64, False),
+    (128, 4096, 14336, "fp16", True, 64, False),
+    (20, 14336, 4096, "bf16", True, 64, False),    # batch between the GEMV route (<= 8) and a full 32-row tile
 ]
 
 

@@ -112,6 +112,44 @@ def test_gemv_block_column_edges(F, dtype, nested, shape):
     assert np.all(np.abs(yk - exact) <= rel * np.abs(exact) + noise * rms)
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("shape", [(28672, 8192), (8192, 28672), (8192, 8192), (1024, 8192)])
+def test_gemv_config5_shapes_row_sample(F, dtype, shape):
+    """BASELINE config 5 (Llama-3-70B linears) at FULL size on the device; the oracle checks a sample of 16-row
+    tiles (first, last, around every 1/148th boundary where a CTA's tile range ends, and random ones) against the
+    fp64-exact product and the reference-faithful chain -- same gates as config 2."""
+    N, K = shape
+    torch.manual_seed(N + K)
+    W = (torch.randn(N, K, device="cuda") * 0.02).to(DT[dtype])
+    x = torch.randn(1, K).to(DT[dtype])
+    q, st = F.quantize_4bit(W, blocksize=64, compress_statistics=True, quant_type="nf4")
+    del W
+    y = F.gemv_4bit(x.cuda(), q.t(), state=st)
+    torch.cuda.synchronize()
+    tiles = N // 16
+    rng = np.random.RandomState(N)
+    pick = {0, 1, tiles - 1, tiles - 2}
+    for b in (1, 37, 74, 111, 147):
+        pick.update({min(tiles - 1, b * tiles // 148), max(0, b * tiles // 148 - 1)})
+    pick.update(rng.randint(0, tiles, 16).tolist())
+    rows = np.concatenate([np.arange(tl * 16, tl * 16 + 16) for tl in sorted(pick)])
+    absmax = orc.denest_absmax(st.absmax.cpu().numpy(), st.state2.absmax.cpu().numpy(), st.state2.code.cpu().numpy(),
+                               np.float32(st.offset.item()), st.state2.blocksize).reshape(N, K // 64)[rows].ravel()
+    qn = q.cpu().numpy().reshape(N, K // 2)[rows].ravel()
+    code = st.code.cpu().numpy()
+    xb = to_bits(x).ravel()
+    exact = orc.gemm_4bit_exact(xb, dtype, qn, absmax, code, 1, len(rows), K, 64)[0]
+    faithful = from_bits(orc.gemv_4bit(xb, dtype, qn, absmax, code, len(rows), K, 64, 0), dtype).double().numpy()
+    yk = y.double().cpu().numpy().ravel()[rows]
+    err_exact, err_ref_chain = rel_l2(yk, exact), rel_l2(faithful, exact)
+    assert err_exact <= TOL_EXACT[dtype], (err_exact,)
+    assert rel_l2(yk, faithful) <= TOL_FAITHFUL[dtype]
+    assert err_exact <= err_ref_chain * 1.05 + 1e-7, (err_exact, err_ref_chain)
+    rms = np.sqrt(np.mean(exact ** 2))
+    rel, noise = {"bf16": (2.0 ** -8, 2.0 ** -7), "fp16": (2.0 ** -11, 2.0 ** -9)}[dtype]
+    assert np.all(np.abs(yk - exact) <= rel * np.abs(exact) + noise * rms)
+
+
 def test_gemv_deterministic(F):
     """Partial sums meet in a fixed order: two launches give bit-identical outputs."""
     W, x, q, st = make_case(F, 4096, 4096, "bf16", seed=5)

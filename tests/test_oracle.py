@@ -279,3 +279,43 @@ def test_llm_int8_forward_restatement_tracks_the_fp32_product():
     # threshold 0: no decomposition, plain int8 path
     y0, CA0, _, idx0 = orc.llm_int8_forward(A, CB, rs, bias, 0.0)
     assert idx0.size == 0 and CA0[:, 17].any()
+
+
+def test_scalar_trees_match_reference_executed_vectors(tables):
+    """tests/golden/ref_device_trees.npz holds outputs of the reference's OWN scalar device functions (bodies cut out
+    of kernel_quant.cpp:519-837 verbatim and compiled by make_golden.py) on ~260 k seeded inputs plus every decision
+    threshold +- 1 ulp, +-0, denormals, inf and NaN.  The oracle's restatements must agree on every input -- this is
+    what pins the NF4 / FP4 trees and dQuantize<0> beyond their constants."""
+    import ctypes as ct
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_mkg", os.path.join(GOLDEN, "make_golden.py"))
+    mkg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mkg)
+    x, code = mkg.tree_inputs()
+    g = np.load(os.path.join(GOLDEN, "ref_device_trees.npz"))
+    assert x.size == int(g["n_inputs"][0]) and int(np.bitwise_xor.reduce(x.view(np.uint32))) == int(g["x_crc"][0])
+    L = orc.lib()
+    L.orc_quantize_nf4_scalar.restype = ct.c_ubyte
+    L.orc_quantize_fp4_scalar.restype = ct.c_ubyte
+    L.orc_quantize_8bit_scalar.restype = ct.c_ubyte
+    L.orc_quantize_nf4_scalar.argtypes = [ct.c_float]
+    L.orc_quantize_fp4_scalar.argtypes = [ct.c_float]
+    L.orc_quantize_8bit_scalar.argtypes = [ct.c_void_p, ct.c_float]
+    step = 1 if os.environ.get("BNB_FULL_TREE_CHECK") else 7          # every 7th random input + ALL the specials
+    n_special = x.size - 260000
+    idx = np.concatenate([np.arange(0, 260000, step), np.arange(260000, x.size)])
+    assert n_special > 1500
+    q_nf4 = np.array([L.orc_quantize_nf4_scalar(float(v)) for v in x[idx]], np.uint8)
+    q_fp4 = np.array([L.orc_quantize_fp4_scalar(float(v)) for v in x[idx]], np.uint8)
+    assert np.array_equal(q_nf4, g["q_nf4"][idx])
+    assert np.array_equal(q_fp4, g["q_fp4"][idx])
+    finite = np.isfinite(x)
+    pos = np.cumsum(finite) - 1                                       # index into the finite-only 8-bit fixture
+    idx8 = idx[finite[idx]]
+    cptr = code.ctypes.data_as(ct.c_void_p)
+    q8 = np.array([L.orc_quantize_8bit_scalar(cptr, float(v)) for v in x[idx8]], np.uint8)
+    assert np.array_equal(q8, g["q_8bit_finite"][pos[idx8]])
+    assert np.array_equal(orc.nf4_table().view(np.uint32), g["deq_nf4"].view(np.uint32))
+    fp4 = np.array([orc.fp4_table()[i] * np.float32(0.73) for i in range(16)], np.float32)
+    # dDequantizeFP4Tree multiplies (c * absmax) * sign left to right: the table at absmax 1 times 0.73 is the same product
+    assert np.array_equal(fp4.view(np.uint32), g["deq_fp4_absmax0p73"].view(np.uint32))
