@@ -39,7 +39,11 @@ for p in (ROOT, PKG_DIR):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-NCU_TRAFFIC_RATIO = 23.306496 / 23.291200   # measured DRAM bytes per algorithmic byte (ncu, 11008x4096 GEMV)
+# DRAM bytes per algorithmic byte of the GEMV kernel: a CONSTANT taken from the committed ncu --set full capture of the
+# named round (dram__bytes_read.sum + dram__bytes_write.sum of one 11008x4096 launch), not measured inside this run
+NCU_TRAFFIC_RATIO = 23.306496 / 23.291200
+NCU_TRAFFIC_SOURCE = "ncu-derived constant, round 1: dram bytes / algorithmic bytes = 1.0007 (profiles/r1_ncu_summaries.txt)"
+GEMV_KERNEL_NAME = "k_gemv4_bc<bf16,nested>"
 LAYER_SHAPES_7B = [(4096, 4096)] * 4 + [(11008, 4096)] * 2 + [(4096, 11008)]
 LAYER_SHAPES_70B = [(8192, 8192), (1024, 8192), (1024, 8192), (8192, 8192), (28672, 8192), (28672, 8192), (8192, 28672)]
 
@@ -131,13 +135,15 @@ _CPU_SAMPLE = {}
 def _cpu_sample():
     """one 4096x4096 layer quantised with the reference's 8-bit dynamic code, blocksize 64 (setup, untimed)"""
     if not _CPU_SAMPLE:
+        import numpy as np
         import torch
         from oracle import oracle as orc
-        from bnb_b200.functional import create_dynamic_map
         N = K = 4096
         torch.manual_seed(0)
         W = (torch.randn(N, K) * 0.02).numpy().ravel()
-        code = create_dynamic_map().numpy()
+        # the reference's own create_dynamic_map() table (fixture generated from the reference source): the reference arm
+        # loads nothing of this repo's product library
+        code = np.ascontiguousarray(np.load(os.path.join(ROOT, "tests", "golden", "ref_python_tables.npz"))["dynamic_map"], dtype=np.float32)
         q, absmax = orc.quantize_blockwise(W, "fp32", code, 64, "8bit")
         kind = "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_cpu.so")) else "port"
         _CPU_SAMPLE.update(N=N, K=K, code=code, q=q, absmax=absmax, x=torch.randn(1, K), kind=kind,
@@ -195,173 +201,136 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--layers", type=int, default=32, help="decoder layers in the stack (32 = the whole Llama-2-7B)")
-    ap.add_argument("--workload", default="llama2-7b", choices=["llama2-7b", "llama3-70b"])
-    ap.add_argument("--batch", type=int, default=1)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
-                    help="N>1: output all-gather fused into the GEMV epilogue (peer stores), or one NCCL all-gather per linear")
-    ap.add_argument("--sync", default="barrier", choices=["kernel", "barrier"],
-                    help="N>1 fused collective: ordering folded into the GEMV kernels, or one symmetric-memory barrier launch per consumer group")
-    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph of the step")
-    ap.add_argument("--barrier", default="pdl", choices=["pdl", "symm"],
-                    help="N>1: consumer-group barrier = cbnb_peer_barrier (a link of the PDL chain) or torch symmetric-memory barrier")
-    ap.add_argument("--no-fuse-same-input", dest="fuse_same_input", action="store_false",
-                    help="N>1: one launch per linear instead of one per group of linears that read the same x (q/k/v, gate/up)")
-    ap.add_argument("--graph-shape", default="chain", choices=["decoder", "chain"],
-                    help="N=1: dependency structure of the step. chain = all launches on one stream, overlapped by "
-                         "programmatic dependent launch (default, measured faster: 2392 vs 2148 GB/s); decoder = the "
-                         "layer's own structure, {q,k,v} in parallel -> o -> {gate,up} in parallel -> down, on three "
-                         "capture streams (cross-stream graph edges are full dependencies without PDL)")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
+DECODER_GROUPS = [[0, 1, 2], [3], [4, 5], [6]]      # q/k/v | o | gate/up | down: linears that read the same x
 
-    if args.impl == "reference":
-        run_reference_arm(args)
-        return
 
-    import numpy as np
+def _timed(fn, steps, warmup, world, dev):
     import torch
     import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def _capture(fn, no_graph=False):
+    """CUDA graph of one step (the inner loop is launch-bound: ~3 us kernels vs ~20 us of Python per call); falls
+    back to eager when capture is not possible."""
+    import torch
+    if no_graph:
+        return fn, False
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        torch.cuda.synchronize()
+        return g.replay, True
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches\n")
+        torch.cuda.synchronize()
+        return fn, False
+
+
+def run_stack(args, workload, layers, full, world, rank, dev, sampler=None):
+    """Build one NF4 linear stack (llama2-7b / llama3-70b shapes), time `steps` passes of gemv_4bit over it.
+    full=True: also the end-to-end number through the public API and the shared-input variant (headline run)."""
+    import torch
+    import torch.distributed as dist
 
     import bnb_b200
     from bnb_b200 import functional as F
     from bnb_b200.parallel import all_gather_features, shard_quantized_weight
 
-    shapes = LAYER_SHAPES_7B if args.workload == "llama2-7b" else LAYER_SHAPES_70B
-    if args.workload == "llama3-70b":
-        args.layers = min(args.layers, 8)      # 8 layers = 3.5 GB of NF4+DQ weights: > L2 per GPU even when sharded 8 ways
+    shapes = LAYER_SHAPES_7B if workload == "llama2-7b" else LAYER_SHAPES_70B
+    if workload == "llama3-70b":
+        layers = min(layers, 8)      # 8 layers = 3.5 GB of NF4+DQ weights: > L2 per GPU even when sharded 8 ways
     dtype = torch.bfloat16
     B = args.batch
 
     # ---- build the quantised stack (full matrices are quantised, then row-sharded: SURVEY 8e)
     torch.manual_seed(1234)
     mats = []       # (packed_shard, state_shard, N, K)
+    full_first = []  # N > 1: the unsharded first layer, for the bit-identity check before timing
     alg_bytes = 0
-    for layer in range(args.layers):
+    for layer in range(layers):
         for (N, K) in shapes:
             W = (torch.randn(N, K, device=dev, dtype=torch.float32) * 0.02).to(dtype)
             q, st = F.quantize_4bit(W, blocksize=64, compress_statistics=True, quant_type="nf4")
             del W
             if world > 1:
+                if layer == 0:
+                    full_first.append((q, st))
                 q, st = shard_quantized_weight(q, st, world, rank)
             mats.append((q, st, N, K))
             alg_bytes += algorithmic_bytes(N, K)
     xs = [torch.randn(B, K, device=dev, dtype=dtype) for (_, _, _, K) in mats]
     outs = [torch.empty(B, st.shape[0], device=dev, dtype=dtype) for (_, st, _, _) in mats]
     gathered = [torch.empty(world, B, st.shape[0], device=dev, dtype=dtype) for (_, st, _, _) in mats] if world > 1 else None
-    n_launch_per_step = len(mats)
+    per_layer = len(shapes)
     # multi-GPU: the output all-gather is fused into the GEMV epilogue (peer stores over NVLink into symmetric
-    # memory); one signal-pad barrier per group of linears that feed the same consumer in a decoder layer
-    # (q/k/v | o | gate/up | down) stands for the point where that consumer would wait.  --collective nccl keeps
-    # the plain NCCL all-gather per linear.
+    # memory); one barrier per group of linears that feed the same consumer in a decoder layer (q/k/v | o | gate/up |
+    # down) stands for the point where that consumer would wait.  --collective nccl keeps one NCCL all-gather per linear.
     peers = None
     collective = "none"
     if world > 1:
         collective = "nccl-allgather-per-linear"
         if args.collective == "fused" and B == 1:
             try:
-                from bnb_b200.parallel import PeerOutputBuffers, sharded_gemv_push
+                from bnb_b200.parallel import PeerOutputBuffers, sharded_gemv_push, sharded_gemv_push_multi
                 peers = PeerOutputBuffers([N for (_, _, N, _) in mats], dtype, dev)
                 collective = "fused-epilogue-p2p-stores+symm-barrier-per-consumer-group"
-                if args.barrier == "pdl" and args.sync != "kernel":
+                if args.barrier == "pdl":
                     peers.enable_fast_barrier()
                     collective = "fused-epilogue-p2p-stores+pdl-chained-peer-barrier-per-consumer-group"
-                if args.sync == "kernel":
-                    peers.enable_kernel_sync(ngroups=args.layers * 4 if len(shapes) == 7 else len(mats))
-                    collective = "fused-epilogue-p2p-stores+in-kernel-signal/wait-per-consumer-group"
             except Exception as e:  # noqa: BLE001
                 sys.stderr.write(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL all-gather\n")
                 peers = None
-    per_layer = len(shapes)
-    group_ends = {2, 3, 5, 6} if per_layer == 7 else set(range(per_layer))
-
-    group_starts = {0, 3, 4, 6} if per_layer == 7 else set(range(per_layer))
-    kernel_sync = peers is not None and args.sync == "kernel"
-    syncs = None
-    if kernel_sync:   # one descriptor per linear: group index, "ends a group" -> signal, "starts a group" -> wait
-        syncs, gi = [], 0
-        for i in range(len(mats)):
-            pos = i % per_layer
-            syncs.append(peers.sync_desc(gi, pos in group_ends, pos in group_starts))
-            if pos in group_ends:
-                gi += 1
-
-    def fused_linear(i, x, q, st):
-        if kernel_sync:
-            sharded_gemv_push(x, q, st, peers, i, syncs[i])
-            if i == len(mats) - 1:
-                peers.bump_epoch()      # next pass counts on: sequence numbers never repeat across graph replays
-        else:
-            sharded_gemv_push(x, q, st, peers, i)
-            if (i % per_layer) in group_ends:
-                peers.barrier()
-
-    # N=1: the linears of a decoder layer that read the same activations (q/k/v, gate/up) do not depend on each other:
-    # they are launched on parallel streams (parallel branches of the captured graph), everything else stays ordered.
-    decoder_groups = [[0, 1, 2], [3], [4, 5], [6]] if per_layer == 7 else [[j] for j in range(per_layer)]
-    structured = world == 1 and args.graph_shape == "decoder" and per_layer == 7
-    side_streams = [torch.cuda.Stream(device=dev) for _ in range(2)] if structured else []
-
-    def run_structured(call):
-        main = torch.cuda.current_stream()
-        for base in range(0, len(mats), per_layer):
-            for grp in decoder_groups:
-                if len(grp) == 1:
-                    call(base + grp[0])
-                    continue
-                fork = torch.cuda.Event()
-                fork.record(main)
-                for j, pos in enumerate(grp):
-                    if j == 0:
-                        call(base + pos)
-                    else:
-                        sst = side_streams[j - 1]
-                        sst.wait_event(fork)
-                        with torch.cuda.stream(sst):
-                            call(base + pos)
-                for j in range(1, len(grp)):
-                    join = torch.cuda.Event()
-                    join.record(side_streams[j - 1])
-                    main.wait_event(join)
-
-    fuse_sharded = peers is not None and not kernel_sync and per_layer == 7 and args.fuse_same_input
+    groups = DECODER_GROUPS if per_layer == 7 else [[j] for j in range(per_layer)]
+    group_ends = {g[-1] for g in groups}
+    fuse_sharded = peers is not None and per_layer == 7 and args.fuse_same_input
     if fuse_sharded:
-        from bnb_b200.parallel import sharded_gemv_push_multi
         collective += "; q/k/v and gate/up share one launch"
 
+    def sharded_step():
+        for base in range(0, len(mats), per_layer):
+            for grp in groups:
+                ids = [base + p for p in grp]
+                if fuse_sharded and len(ids) > 1:
+                    sharded_gemv_push_multi(xs[ids[0]], [mats[i][0] for i in ids], [mats[i][1] for i in ids], peers, ids)
+                else:
+                    for i in ids:
+                        sharded_gemv_push(xs[i], mats[i][0], mats[i][1], peers, i)
+                peers.barrier()
+
     def step_eager():
-        if fuse_sharded:     # N-sharded: one launch per group of linears that read the same x, one barrier per group
-            for base in range(0, len(mats), per_layer):
-                for grp in decoder_groups:
-                    ids = [base + p for p in grp]
-                    if len(ids) == 1:
-                        sharded_gemv_push(xs[ids[0]], mats[ids[0]][0], mats[ids[0]][1], peers, ids[0])
-                    else:
-                        sharded_gemv_push_multi(xs[ids[0]], [mats[i][0] for i in ids], [mats[i][1] for i in ids], peers, ids)
-                    peers.barrier()
-            return
-        if structured and B == 1:
-            run_structured(lambda i: F.gemv_4bit(xs[i], mats[i][0].t(), out=outs[i], state=mats[i][1]))
+        if peers is not None:
+            sharded_step()
             return
         for i, (q, st, N, K) in enumerate(mats):
-            if peers is not None:
-                fused_linear(i, xs[i], q, st)
-                continue
             if B == 1:
                 F.gemv_4bit(xs[i], q.t(), out=outs[i], state=st)
             else:
@@ -369,32 +338,75 @@ def main():
             if world > 1:
                 all_gather_features(outs[i], world, None, gathered[i])
 
-    def capture(fn):
-        """CUDA graph of one step (the inner loop is launch-bound: ~3 us kernels vs ~20 us of Python per
-        call); falls back to eager when capture is not possible."""
-        if args.no_graph:
-            return fn, False
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(3):
-                    fn()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                fn()
-            torch.cuda.synchronize()
-            return g.replay, True
-        except Exception as e:  # noqa: BLE001
-            sys.stderr.write(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches\n")
-            torch.cuda.synchronize()
-            return fn, False
+    # ---- N > 1: every rank's gathered vectors must be bit-identical to the single-GPU kernel on the full matrix
+    parity_checked = None
+    if peers is not None:
+        peers.buf.zero_()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sharded_step()
+        peers.barrier()
+        torch.cuda.synchronize()
+        ok = True
+        for i, (qf, stf) in enumerate(full_first):
+            ref = F.gemv_4bit(xs[i], qf.t(), state=stf)
+            ok = ok and torch.equal(ref.view(torch.int16), peers.full(i).view(torch.int16))
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity_checked = bool(int(flag.item()))
+        if not parity_checked:
+            raise SystemExit("[bench] N-sharded outputs differ from the single-GPU kernel: not timing a wrong result")
+        del full_first[:]
 
-    step_kernel_only, graphed = capture(step_eager)
+    step_kernel_only, graphed = _capture(step_eager, args.no_graph)
+    if peers is not None:
+        launches_per_step = (len(mats) // per_layer) * (len(groups) if fuse_sharded else per_layer)
+        our_kernels_per_step = launches_per_step + (len(mats) // per_layer) * len(groups)      # + one barrier kernel per group
+    else:
+        launches_per_step = our_kernels_per_step = len(mats)
 
-    # ---- e2e buffers: pinned host activations in, outputs back
+    res = {"workload": workload, "layers": layers, "alg_bytes": alg_bytes, "n_gemv": len(mats), "graphed": graphed,
+           "collective": collective, "launches_per_step": launches_per_step, "our_kernels_per_step": our_kernels_per_step,
+           "parity_checked": parity_checked, "batch": B}
+
+    if sampler is not None:
+        sampler.start()
+        sampler.timed.set()
+    ms_total = _timed(step_kernel_only, args.steps, args.warmup, world, dev)
+    if sampler is not None:
+        # the timed region lasts tens of ms: keep the same load running ~0.3 s longer so the clock record has enough
+        # samples of the GPU under exactly this load (these extra steps are not part of any number)
+        pass
+    if full:
+        for _ in range(min(2000, max(1, int(300.0 / max(ms_total / args.steps, 1e-3))))):
+            step_kernel_only()
+        torch.cuda.synchronize()
+    if sampler is not None:
+        sampler.timed.clear()
+        sampler.stop_flag.set()
+    res["ms_per_step"] = ms_total / args.steps
+    if not full:
+        return res
+
+    # ---- additive: the linears of a layer that read the same activations (q/k/v, gate/up) in ONE launch each
+    # (cgemm_4bit_inference_nested_multi_*): 4 launches per layer instead of 7.  Reported beside the per-call metric.
+    if world == 1 and B == 1 and per_layer == 7:
+        def step_fused():
+            for base in range(0, len(mats), per_layer):
+                for grp in groups:
+                    ids = [base + p for p in grp]
+                    if len(ids) == 1:
+                        i = ids[0]
+                        F.gemv_4bit(xs[i], mats[i][0].t(), out=outs[i], state=mats[i][1])
+                    else:
+                        F.gemv_4bit_multi(xs[ids[0]], [mats[i][0].t() for i in ids], [mats[i][1] for i in ids],
+                                          outs=[outs[i] for i in ids])
+        fused_step, _ = _capture(step_fused, args.no_graph)
+        res["fused_launches"] = (len(mats) // per_layer) * len(groups)
+        res["fused_bytes"] = alg_bytes - sum((len(g) - 1) * 2 * mats[g[0]][3] for g in groups) * (len(mats) // per_layer)
+        res["fused_ms"] = _timed(fused_step, args.steps, args.warmup, world, dev) / args.steps
+
+    # ---- e2e: public API end to end: pinned host activations -> device, Linear4bit's matmul_4bit per matrix, outputs -> host
     k_total = sum(K for (_, _, _, K) in mats)
     n_total = sum(N for (_, _, N, _) in mats)
     x_host = torch.randn(B, k_total).to(dtype).pin_memory()
@@ -407,40 +419,38 @@ def main():
         offs_k.append(offs_k[-1] + K)
 
     def e2e_body():
-        # public API end to end: pinned host activations -> device, Linear4bit's matmul_4bit per matrix, outputs -> host
         x_dev.copy_(x_host, non_blocking=True)
-        if structured and B == 1:
-            run_structured(lambda i: bnb_b200.matmul_4bit(x_dev[:, offs_k[i]:offs_k[i + 1]], mats[i][0].t(), quant_state=mats[i][1],
-                                                          out=y_dev[:, offs_n[i]:offs_n[i + 1]]))
-            y_host.copy_(y_dev, non_blocking=True)
-            return
-        ko = no = 0
-        for i, (q, st, N, K) in enumerate(mats):
-            if peers is not None:
-                fused_linear(i, x_dev[:, ko:ko + K], q, st)
+        if peers is not None:
+            for base in range(0, len(mats), per_layer):
+                for grp in groups:
+                    ids = [base + p for p in grp]
+                    xv = x_dev[:, offs_k[ids[0]]:offs_k[ids[0] + 1]]
+                    if fuse_sharded and len(ids) > 1:
+                        sharded_gemv_push_multi(xv, [mats[i][0] for i in ids], [mats[i][1] for i in ids], peers, ids)
+                    else:
+                        for i in ids:
+                            sharded_gemv_push(x_dev[:, offs_k[i]:offs_k[i + 1]], mats[i][0], mats[i][1], peers, i)
+                    peers.barrier()
+            if peers.offsets[-1] + peers.sizes[-1] == n_total:
+                y_host.copy_(peers.buf[:n_total].view(B, n_total), non_blocking=True)   # gathered vectors, straight from symmetric memory
             else:
-                if world == 1 and B == 1:
-                    # `out=` is part of the reference signature (matmul_4bit(A, B, quant_state, out, bias)): the GEMV
-                    # writes straight into its slice of the step's output buffer
-                    bnb_b200.matmul_4bit(x_dev[:, ko:ko + K], q.t(), quant_state=st, out=y_dev[:, no:no + N])
-                else:
-                    y = bnb_b200.matmul_4bit(x_dev[:, ko:ko + K], q.t(), quant_state=st)
-                    if world > 1:
-                        y = all_gather_features(y, world)
-                    y_dev[:, no:no + N] = y.reshape(B, N)
-            ko += K
-            no += N
-        if kernel_sync:
-            peers.barrier()      # the host read below consumes every gathered vector of the pass
-        if peers is not None and peers.offsets[-1] + peers.sizes[-1] == n_total:
-            y_host.copy_(peers.buf[:n_total].view(B, n_total), non_blocking=True)   # gathered vectors, straight from symmetric memory
-        else:
-            if peers is not None:
                 for j, (_, _, Nj, _) in enumerate(mats):
                     y_dev[:, offs_n[j]:offs_n[j] + Nj] = peers.full(j)
-            y_host.copy_(y_dev, non_blocking=True)
+                y_host.copy_(y_dev, non_blocking=True)
+            return
+        for i, (q, st, N, K) in enumerate(mats):
+            if world == 1 and B == 1:
+                # `out=` is part of the reference signature (matmul_4bit(A, B, quant_state, out, bias)): the GEMV
+                # writes straight into its slice of the step's output buffer
+                bnb_b200.matmul_4bit(x_dev[:, offs_k[i]:offs_k[i + 1]], q.t(), quant_state=st, out=y_dev[:, offs_n[i]:offs_n[i + 1]])
+            else:
+                y = bnb_b200.matmul_4bit(x_dev[:, offs_k[i]:offs_k[i + 1]], q.t(), quant_state=st)
+                if world > 1:
+                    y = all_gather_features(y, world)
+                y_dev[:, offs_n[i]:offs_n[i + 1]] = y.reshape(B, N)
+        y_host.copy_(y_dev, non_blocking=True)
 
-    e2e_launch, e2e_graphed = capture(e2e_body)
+    e2e_launch, e2e_graphed = _capture(e2e_body, args.no_graph)
 
     def step_e2e():
         e2e_launch()
@@ -452,57 +462,6 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
-
-    # ---- additive: the linears of a layer that read the same activations (q/k/v, gate/up) in ONE launch each
-    # (cgemm_4bit_inference_nested_multi_*): 4 launches per layer instead of 7.  Reported beside the per-call metric.
-    fused_step = None
-    if world == 1 and B == 1 and per_layer == 7:
-        def step_fused():
-            for base in range(0, len(mats), per_layer):
-                for grp in decoder_groups:
-                    ids = [base + p for p in grp]
-                    if len(ids) == 1:
-                        i = ids[0]
-                        F.gemv_4bit(xs[i], mats[i][0].t(), out=outs[i], state=mats[i][1])
-                    else:
-                        F.gemv_4bit_multi(xs[ids[0]], [mats[i][0].t() for i in ids], [mats[i][1] for i in ids],
-                                          outs=[outs[i] for i in ids])
-        fused_step, fused_graphed = capture(step_fused)
-        fused_launches = (len(mats) // per_layer) * len(decoder_groups)
-        fused_bytes = alg_bytes - sum((len(g) - 1) * 2 * mats[g[0]][3] for g in decoder_groups) * (len(mats) // per_layer)
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        sampler.timed.set()
-    ms_total = timed(step_kernel_only, args.steps, args.warmup)
-    # the timed region lasts tens of ms: keep the same load running ~0.3 s longer so the clock record has enough
-    # samples of the GPU under exactly this load (these extra steps are not part of any number; every rank runs
-    # the same count, ms_total being the max over ranks)
-    for _ in range(min(2000, max(1, int(300.0 / max(ms_total / args.steps, 1e-3))))):
-        step_kernel_only()
-    torch.cuda.synchronize()
-    if rank == 0:
-        sampler.timed.clear()
-        sampler.stop_flag.set()
-    fused_ms = timed(fused_step, args.steps, args.warmup) / args.steps if fused_step is not None else None
-    # e2e: host timer around the same loop (copies + API calls + sync are inside)
     for _ in range(2):
         step_e2e()
     barrier()
@@ -516,46 +475,215 @@ def main():
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    res.update(e2e_s_per_step=e2e_s / e2e_steps, e2e_graphed=e2e_graphed, h2d=x_host.numel() * 2, d2h=y_host.numel() * 2)
+    return res
+
+
+def run_igemmlt_extras(steps, warmup):
+    """BASELINE metric component 2: int8 igemmlt TOPS on config 3 (4096 tokens x 4096 -> 16384, threshold 6.0), through the
+    reference ABI (cigemmlt_turing_32: col32 x col_turing -> col32 int32), the B200-native row-major entry
+    (cigemm_rowmajor_32) and the fused Linear8bitLt.forward.  Rank 0, one GPU, outside the headline's timed region."""
+    import torch
+
+    import bnb_b200
+    from bnb_b200 import functional as F
+
+    m, k, n = 4096, 4096, 16384
+    ops = 2.0 * m * n * k
+    peak_bf16 = 1551.4
+    try:
+        peak_bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        pass
+    torch.manual_seed(3)
+    CA = torch.randint(-127, 128, (m, k), dtype=torch.int8, device="cuda")
+    CB = torch.randint(-127, 128, (n, k), dtype=torch.int8, device="cuda")
+    out32 = torch.empty(m, n, dtype=torch.int32, device="cuda")
+    C32A, SA = F.transform(CA, "col32")
+    CxB, SB = F.transform(CB, "col_turing")
+    o32, So = F.igemmlt(C32A, CxB, SA, SB)
+    A16 = torch.randn(m, k, device="cuda").half()
+    A16[:, [7, 100, 2000, 3000]] = 8.0                  # four outlier feature columns (>= threshold 6.0)
+    lin = bnb_b200.nn.Linear8bitLt(k, n, bias=True, has_fp16_weights=False, threshold=6.0).cuda().half()
+    CA_host = CA.cpu().pin_memory()
+    A16_host = A16.cpu().pin_memory()
+    y_host = torch.empty(16, n, dtype=torch.float16).pin_memory()
+    c_host = torch.empty(16 * n, dtype=torch.int32).pin_memory()
+
+    def ev_time(fn, reps):
+        for _ in range(max(3, warmup)):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def host_time(fn, reps):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e3
+
+    def entry(ms, ms_e2e, h2d, d2h, api, launches):
+        tops = ops / (ms * 1e-3) / 1e12
+        return {"TOPS": tops, "ms": ms, "ops": ops, "api": api, "gpu_launches_per_call": launches,
+                "roofline": {"bound": "tensor", "achieved": tops, "unit": "TOP/s",
+                             "peak_2x_measured_bf16": 2 * peak_bf16, "frac_of_2x_measured_bf16": tops / (2 * peak_bf16),
+                             "peak_nominal_int8": 4500.0, "frac_of_nominal_int8": tops / 4500.0},
+                "e2e": {"value": ops / (ms_e2e * 1e-3) / 1e12, "unit": "TOP/s", "ms": ms_e2e, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "note": "operand A from pinned host memory in, first 16 output rows back"}}
+
+    reps = max(5, min(20, steps))
+    out = {"config": "4096 tokens x (4096 -> 16384), int8, threshold 6.0 (BASELINE config 3)", "l2": "operands + output 352 MB > L2"}
+    with torch.no_grad():
+        # (1) reference ABI
+        f1 = lambda: F.igemmlt(C32A, CxB, SA, SB, out=o32, Sout=So)   # noqa: E731
+
+        def f1e():
+            C32A.view(-1)[: m * k].copy_(CA_host.view(-1), non_blocking=True)   # same bytes, any layout: the copy is what is timed
+            F.igemmlt(C32A, CxB, SA, SB, out=o32, Sout=So)
+            c_host.copy_(o32.view(-1)[: 16 * n], non_blocking=True)
+        out["cigemmlt_turing_32"] = entry(ev_time(f1, reps), host_time(f1e, reps), m * k, 16 * n * 4,
+                                          "F.igemmlt(col32, col_turing) -> cigemmlt_turing_32 (reference ABI, pythonInterface.cpp:298)", None)
+        # (2) row-major entry
+        f2 = lambda: F.igemmlt(CA, CB, ((m, k), "row"), ((n, k), "row"), out=out32, Sout=((m, n), "row"))   # noqa: E731
+
+        def f2e():
+            CA.copy_(CA_host, non_blocking=True)
+            F.igemmlt(CA, CB, ((m, k), "row"), ((n, k), "row"), out=out32, Sout=((m, n), "row"))
+            c_host.copy_(out32.view(-1)[: 16 * n], non_blocking=True)
+        out["cigemm_rowmajor_32"] = entry(ev_time(f2, reps), host_time(f2e, reps), m * k, 16 * n * 4,
+                                          "F.igemmlt(row, row) -> cigemm_rowmajor_32 (additive, TMA-native layout)", 1)
+        # (3) fused Linear8bitLt forward (quantise + outliers + GEMM + dequant epilogue)
+        f3 = lambda: lin(A16)   # noqa: E731
+
+        def f3e():
+            A16.copy_(A16_host, non_blocking=True)
+            y = lin(A16)
+            y_host.copy_(y[:16], non_blocking=True)
+        out["linear8bitlt_forward"] = entry(ev_time(f3, reps), host_time(f3e, reps), m * k * 2, 16 * n * 2,
+                                            "bnb_b200.nn.Linear8bitLt.forward (has_fp16_weights=False, threshold 6.0, bias)", None)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--layers", type=int, default=32, help="decoder layers in the stack (32 = the whole Llama-2-7B)")
+    ap.add_argument("--workload", default="llama2-7b", choices=["llama2-7b", "llama3-70b"])
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the igemmlt and 70B-stack extra keys")
+    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
+                    help="N>1: output all-gather fused into the GEMV epilogue (peer stores), or one NCCL all-gather per linear")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph of the step")
+    ap.add_argument("--barrier", default="pdl", choices=["pdl", "symm"],
+                    help="N>1: consumer-group barrier = cbnb_peer_barrier (a link of the PDL chain) or torch symmetric-memory barrier")
+    ap.add_argument("--no-fuse-same-input", dest="fuse_same_input", action="store_false",
+                    help="N>1: one launch per linear instead of one per group of linears that read the same x (q/k/v, gate/up)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    head = run_stack(args, args.workload, args.layers, True, world, rank, dev, sampler)
+    torch.cuda.empty_cache()
+
+    extras = {}
+    if not args.no_extras and args.batch == 1:
+        if args.workload == "llama2-7b":
+            try:
+                r70 = run_stack(args, "llama3-70b", 8, False, world, rank, dev)
+                gbs = r70["alg_bytes"] / (r70["ms_per_step"] * 1e-3) / 1e9
+                extras["llama3_70b"] = {
+                    "value": gbs, "unit": "GB/s", "ms_per_step": r70["ms_per_step"], "layers": r70["layers"], "n_gpus": world,
+                    "tok_per_s": 1e3 / (r70["ms_per_step"] * 80.0 / r70["layers"]),
+                    "tok_per_s_note": "batch-1 decode rate of the 80-layer Llama-3-70B LINEAR stack (q/k/v/o/gate/up/down NF4 GEMVs "
+                                      "only; attention, norms and sampling are outside SURVEY section 8), extrapolated from the timed "
+                                      f"{r70['layers']}-layer stack",
+                    "algorithmic_bytes_per_step": r70["alg_bytes"], "launches_per_step": r70["launches_per_step"],
+                    "collective": r70["collective"], "parity_checked": r70["parity_checked"],
+                    "frac_of_hbm_peak_per_gpu": gbs / world / measured_peak_gbs()[0]}
+            except Exception as e:  # noqa: BLE001
+                extras["llama3_70b"] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            try:
+                extras["igemmlt"] = run_igemmlt_extras(args.steps, args.warmup)
+            except Exception as e:  # noqa: BLE001
+                extras["igemmlt"] = {"error": f"{type(e).__name__}: {e}"}
+        if world > 1:
+            dist.barrier()
 
     if rank == 0:
-        ms_per_step = ms_total / args.steps
+        ms_per_step = head["ms_per_step"]
+        alg_bytes = head["alg_bytes"]
         value = alg_bytes / (ms_per_step * 1e-3) / 1e9
         peak, peak_kind = measured_peak_gbs()
-        # dominant kernel: one launch == one GEMV; bytes per launch averaged over the stack (per rank)
-        bytes_per_launch = alg_bytes / n_launch_per_step / world
-        launch_ms = ms_per_step / n_launch_per_step
+        # dominant kernel: the GEMV; bytes per launch and launch time averaged over the launches actually issued (per rank)
+        bytes_per_launch = alg_bytes / head["launches_per_step"] / world
+        launch_ms = ms_per_step / head["launches_per_step"]
         achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+        B = args.batch
         line = {
             "metric": "nf4_gemv_4bit_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.workload}-nf4-gemv-b{B}", "layers": args.layers, "gemvs_per_step": n_launch_per_step,
+            "config": {"workload": f"{args.workload}-nf4-gemv-b{B}", "layers": head["layers"], "gemvs_per_step": head["n_gemv"],
                        "blocksize": 64, "nested_absmax": True, "algorithmic_bytes_per_step": alg_bytes,
                        "l2": f"inputs larger than L2 ({alg_bytes / 1e6:.0f} MB of weights per step, distinct per launch)",
-                       "launch": "cuda-graph" if graphed else "eager",
-                       "graph_shape": ("decoder: {q,k,v} parallel -> o -> {gate,up} parallel -> down" if structured and B == 1 else "chain"),
-                       "parallelism": f"n-shard{world}" if world > 1 else "single", "collective": collective},
+                       "launch": "cuda-graph" if head["graphed"] else "eager", "graph_shape": "chain",
+                       "parallelism": f"n-shard{world}" if world > 1 else "single", "collective": head["collective"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         # dram__bytes_read+write per launch of this kernel from the committed ncu --set full capture
-                         # (profiles/r1_ncu_summaries.txt: 23.306 MB for the 23.291 MB 11008x4096 GEMV, 121.23 MB
-                         # for the 121.24 MB 28672x8192 one): DRAM traffic == algorithmic bytes (+0.07 %)
                          "traffic": bytes_per_launch * NCU_TRAFFIC_RATIO if B == 1 else None,
-                         "traffic_source": "ncu dram bytes / algorithmic bytes = 1.0007 (profiles/r1_ncu_summaries.txt)",
-                         "kernel": "k_gemv4_bc<bf16,nested>", "peak_source": peak_kind,
-                         "bytes_per_launch": bytes_per_launch, "launch_us": launch_ms * 1e3},
-            "e2e": {"value": alg_bytes / (e2e_s / e2e_steps) / 1e9, "unit": "GB/s",
-                    "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": y_host.numel() * 2,
-                    "launch": "cuda-graph" if e2e_graphed else "eager",
+                         "traffic_source": NCU_TRAFFIC_SOURCE,
+                         "kernel": GEMV_KERNEL_NAME, "peak_source": peak_kind,
+                         "bytes_per_launch": bytes_per_launch, "launch_us": launch_ms * 1e3,
+                         "launches_per_step": head["launches_per_step"]},
+            "e2e": {"value": alg_bytes / head["e2e_s_per_step"] / 1e9, "unit": "GB/s",
+                    "h2d_bytes_per_step": head["h2d"], "d2h_bytes_per_step": head["d2h"],
+                    "launch": "cuda-graph" if head["e2e_graphed"] else "eager",
                     "api": "bnb_b200.matmul_4bit (Linear4bit.forward path), pinned host x in, y out"},
-            "gpu_launches": n_launch_per_step * args.steps,
+            "gpu_launches": head["our_kernels_per_step"] * args.steps,
             "clocks": sampler.summary(),
         }
-        if fused_ms is not None:
+        if head["parity_checked"] is not None:
+            line["parity_checked"] = head["parity_checked"]
+        if "fused_ms" in head:
+            fv = head["fused_bytes"] / (head["fused_ms"] * 1e-3) / 1e9
             line["fused_same_input"] = {
-                "value": fused_bytes / (fused_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": fused_ms,
-                "launches_per_step": fused_launches, "frac_of_hbm_peak": fused_bytes / (fused_ms * 1e-3) / 1e9 / peak,
+                "value": fv, "unit": "GB/s", "ms_per_step": head["fused_ms"],
+                "launches_per_step": head["fused_launches"], "frac_of_hbm_peak": fv / peak,
                 "api": "bnb_b200.functional.gemv_4bit_multi: q/k/v and gate/up of a layer share one launch "
                        "(bit-identical outputs); NOT the headline value, which stays one call per matrix"}
+        line.update(extras)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_reference_gemv()
         elif not args.no_cpu_baseline:

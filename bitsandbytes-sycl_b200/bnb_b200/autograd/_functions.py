@@ -1,3 +1,8 @@
+# Derived from python_src_quants/autograd/_functions.py of abhilash1910/bitsandbytes-SYCL (itself bitsandbytes,
+# Copyright (c) Facebook, Inc. and its affiliates, MIT license -- see the LICENSE file of that repository).
+# This file keeps the reference's public interface (MatMul4Bit / MatMul8bitLt / MatmulLtState, their dispatch rules and forward/backward step order) because it is
+# the wire / API contract of the drop-in; "xpu" became "cuda" and everything below the interface calls the native
+# sm_100a library.  It is a derived host-side shim, not from-scratch work -- the from-scratch work is csrc/.
 """Forward paths of the reference's python_src_quants/autograd/_functions.py, re-hosted on the B200 kernels:
 MatMul4Bit (:486-540), MatMul8bitLt (:288-483), MatmulLtState (:246-285), matmul (:543-554),
 matmul_4bit (:557-577).  Dispatch rules are the reference's; what runs underneath is native:
@@ -6,8 +11,8 @@ matmul_4bit (:557-577).  Dispatch rules are the reference's; what runs underneat
   * int8     -> double_quant -> ONE fused tcgen05 kind::i8 GEMM with the mm_dequant epilogue
                 (reference: transform + igemmlt + mm_dequant = 3 launches and a 400 MB int32 round trip),
                 outliers (threshold > 0) via the 16-bit side GEMM exactly as the reference does.
-Backward (training) is the "next" row of SURVEY.md 8f: MatMul4Bit keeps the reference's dequant+matmul
-backward; MatMul8bitLt backward is not part of this round.
+Backward: MatMul4Bit keeps the reference's dequant + matmul backward; MatMul8bitLt.backward follows the
+reference's step order (:436-483) on the row-major int8 GEMM.
 """
 import warnings
 from dataclasses import dataclass
@@ -225,9 +230,8 @@ class MatMul4Bit(torch.autograd.Function):
                 return torch.empty(A.shape[:-1] + B_shape[1:], dtype=A.dtype, device=A.device)
             return torch.empty(A.shape[:-1] + B_shape[:1], dtype=A.dtype, device=A.device)
 
-        output = None
-        if not any(ctx.needs_input_grad[:2]) or True:
-            output = F.gemm_4bit(A, B, quant_state, bias=bias)
+        # the fused kernel is the forward in training too: its operand is bit-identical to dequantize_4bit's output
+        output = F.gemm_4bit(A, B, quant_state, bias=bias)
         if output is None:
             output = torch.nn.functional.linear(A, F.dequantize_4bit(B, quant_state).to(A.dtype).t(), bias)
 

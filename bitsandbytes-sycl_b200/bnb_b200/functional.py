@@ -1,3 +1,8 @@
+# Derived from python_src_quants/functional.py of abhilash1910/bitsandbytes-SYCL (itself bitsandbytes,
+# Copyright (c) Facebook, Inc. and its affiliates, MIT license -- see the LICENSE file of that repository).
+# This file keeps the reference's public interface (function names, argument meaning, asserts, QuantState.as_dict/from_dict wire format, create_dynamic_map) because it is
+# the wire / API contract of the drop-in; "xpu" became "cuda" and everything below the interface calls the native
+# sm_100a library.  It is a derived host-side shim, not from-scratch work -- the from-scratch work is csrc/.
 """Host-side mirror of the reference's python_src_quants/functional.py for the quantized-linear hot path.
 
 Same function names, argument meaning and error behaviour as the reference (file:line cited per function,
@@ -481,7 +486,8 @@ def gemv_4bit(A: Tensor, B: Tensor, out: Optional[Tensor] = None, transposed_A=F
     A = A.contiguous()
     code = state.code.to(A.device)
     fused = (FUSED_NESTED_GEMV and state.nested and A.dtype in (torch.float16, torch.bfloat16)
-             and k % 64 == 0 and state.blocksize % 64 == 0 and A.shape[-1] == k)
+             and k % 64 == 0 and state.blocksize % 64 == 0 and A.shape[-1] == k
+             and A.data_ptr() % 16 == 0 and B.data_ptr() % 8 == 0)     # what the native fast path needs; else the reference-shaped route
     if fused:
         s2 = state.state2
         offset = getattr(state, "_offset_host", None)
@@ -505,8 +511,6 @@ def gemv_4bit(A: Tensor, B: Tensor, out: Optional[Tensor] = None, transposed_A=F
                 ct.c_int32(lda), ct.c_int32(ldb), ct.c_int32(ldc), ct.c_int32(state.blocksize), ct.c_int32(s2.blocksize),
                 arr, ct.c_int32(len(peer_outs)), ct.byref(sync) if sync is not None else None)
             post_call(prev)
-            if lib.cbnb_last_error():
-                raise RuntimeError(lib.cbnb_last_error_string().decode())
             return out
         getattr(lib, f"cgemm_4bit_inference_nested_{_SUFFIX[A.dtype]}")(
             ct.c_int32(m), ct.c_int32(n), ct.c_int32(k), get_ptr(A), get_ptr(B), get_ptr(state.absmax),
@@ -542,10 +546,11 @@ def gemv_4bit_multi(A: Tensor, Bs, states, outs=None, peer_outs=None):
                   and st.state2.blocksize == s0.state2.blocksize for st in states)
           and s0.shape[1] % 256 == 0 and A.shape[-1] == s0.shape[1])
     if ok:
-        same = getattr(s0, "_multi_code2_checked", None)
-        if same is None:   # the shared dynamic map: checked once per group (all bitsandbytes states use the same one)
-            same = s0._multi_code2_checked = all(torch.equal(st.state2.code, s0.state2.code) for st in states[1:])
-        ok = same
+        key = tuple(id(st) for st in states)
+        cache = getattr(s0, "_multi_code2_checked", None)
+        if cache is None or cache[0] != key:   # the shared dynamic map: checked once per group of states
+            cache = s0._multi_code2_checked = (key, all(torch.equal(st.state2.code, s0.state2.code) for st in states[1:]))
+        ok = cache[1]
     if not ok:
         return [gemv_4bit(A, B, out=o, state=st, peer_outs=(peer_outs[i] if peer_outs else None))
                 for i, (B, st, o) in enumerate(zip(Bs, states, outs))]
@@ -600,7 +605,11 @@ def gemm_4bit(A: Tensor, B: Tensor, state: QuantState, bias: Optional[Tensor] = 
         return None
     if state.dtype not in (A.dtype, torch.float32):
         return None     # reference: dequantize to state.dtype, then .to(A.dtype) -- two roundings the fused kernel does not do
+    if len(state.shape) != 2 or B.dim() != 2 or B.shape[0] != 1:
+        return None     # un-transposed packed weight: the reference computes A @ W there, not A @ W^T
     N, K = state.shape
+    if A.shape[-1] != K:
+        return None     # wrong activation width: the reference route raises the shape error of F.linear
     A2 = A.reshape(-1, A.shape[-1]).contiguous()
     batch = A2.shape[0]
     if (2 <= batch <= 8 and bias is None and state.nested and FUSED_NESTED_GEMV and K % 64 == 0 and N % 16 == 0
@@ -780,15 +789,49 @@ def transform(A, to_order, from_order="row", out=None, transpose=False, state=No
         dim1, dim2 = ct.c_int32(shape[0]), ct.c_int32(shape[1])
     else:
         dim1, dim2 = ct.c_int32(shape[0] * shape[1]), ct.c_int32(shape[2])
-    fn = {"col32": "col32", "col_turing": "turing", "col_ampere": "ampere"}.get(to_order)
-    if fn is None or from_order != "row":
+    names = {"col32": "col32", "col_turing": "turing", "col_ampere": "ampere"}
+    if to_order == "row" and from_order in names and not transpose:
+        # inverse layouts (reference :2645-2647 calls ctransform_turing2row / ctransform_ampere2row)
+        sym = f"ctransform_{names[from_order]}2row"
+    elif to_order in names and from_order == "row":
+        sym = f"ctransform_row2{names[to_order]}{'T' if transpose else ''}"
+    else:
         raise NotImplementedError(f"Transform function not implemented: From {from_order} to {to_order}")
     A = A.contiguous()
     prev = pre_call(A.device)
     is_on_gpu([A, out])
-    getattr(lib, f"ctransform_row2{fn}{'T' if transpose else ''}")(get_ptr(A), get_ptr(out), dim1, dim2)
+    getattr(lib, sym)(get_ptr(A), get_ptr(out), dim1, dim2)
     post_call(prev)
     return out, new_state
+
+
+def undo_layout_to_row(weight: Tensor, weight_format: str, rows: Optional[int] = None, cols: Optional[int] = None) -> Tensor:
+    """An int8 weight stored in col32 / col_turing / col_ampere (a checkpoint written from `state.CxB`, reference
+    nn/modules.py:725-796) back to row-major [rows, cols]: the inverse of kTransformRowToFormat's index maps
+    (kernel_quant.cpp:3673-3675, 3740-3755, 3822-3832 == blas_utils.h:244-346), as views + one in-tile gather, on
+    whatever device the tensor lives (state dicts are usually loaded on the CPU).  Plays the role of the reference's
+    undo_layout(weight, get_tile_inds(...)) (autograd/_functions.py:89-104)."""
+    R, C = weight.shape[-2], weight.shape[-1]
+    flat = weight.reshape(-1)
+    assert C % 32 == 0, "formatted weights are padded to 32 columns"
+    if weight_format == "col32":
+        out = flat.view(C // 32, R, 32).permute(1, 0, 2).reshape(R, C)
+    elif weight_format == "col_turing":
+        assert R % 8 == 0, "col_turing pads rows to 8"
+        r8 = torch.arange(8, device=weight.device).view(8, 1)
+        c32 = torch.arange(32, device=weight.device).view(1, 32)
+        w = torch.where(r8 % 2 == 1, 128 + (r8 - 1) * 2, r8 * 2) + (c32 // 4) * 16 + (c32 % 4)     # offset inside the 8x32 tile
+        out = flat.view(C // 32, R // 8, 256)[:, :, w.reshape(-1)].view(C // 32, R // 8, 8, 32).permute(1, 2, 0, 3).reshape(R, C)
+    elif weight_format == "col_ampere":
+        assert R % 32 == 0, "col_ampere pads rows to 32"
+        lr = torch.arange(32, device=weight.device)
+        ar = ((lr % 8) // 2) * 8 + (lr // 8) * 2 + (lr % 2)                                        # tile row of logical row lr
+        out = flat.view(C // 32, R // 32, 32, 32)[:, :, ar, :].permute(1, 2, 0, 3).reshape(R, C)
+    else:
+        raise ValueError(f"Unrecognized weights format {weight_format}")
+    rows = R if rows is None else rows
+    cols = C if cols is None else cols
+    return out[:rows, :cols].contiguous()
 
 
 def igemmlt(A, B, SA, SB, out=None, Sout=None, dtype=torch.int32):
@@ -905,9 +948,6 @@ def int8_linear_dequant(CA: Tensor, CB: Tensor, SCA: Tensor, SCB: Tensor, bias: 
     return out
 
 
-_INT8_WS: Dict[Any, Any] = {}
-
-
 def int8_linear_fused(A: Tensor, CB: Tensor, SCB: Tensor, bias: Optional[Tensor] = None, threshold: float = 6.0,
                       out: Optional[Tensor] = None, return_quantized: bool = False):
     """ADDITIVE: the whole LLM.int8 inference forward (MatMul8bitLt.forward, reference _functions.py:292-434, with
@@ -923,17 +963,23 @@ def int8_linear_fused(A: Tensor, CB: Tensor, SCB: Tensor, bias: Optional[Tensor]
     n = CB.shape[0]
     if k % 16 != 0 or CB.shape[1] != k or not CB.is_contiguous():
         return None
-    key = (A.device, m, n, k)
-    ws = _INT8_WS.get(key)
-    if ws is None:
-        dev = A.device
-        ws = dict(CA=torch.empty((m, k), dtype=torch.int8, device=dev), SCA=torch.empty(m, dtype=torch.float32, device=dev),
-                  colflag=torch.zeros(k, dtype=torch.uint8, device=dev), pos=torch.empty(k, dtype=torch.int16, device=dev),
-                  idx=torch.zeros(max(k, 16), dtype=torch.int32, device=dev), count=torch.zeros(1, dtype=torch.int32, device=dev),
-                  subA=torch.empty((m, 16), dtype=torch.float16, device=dev), subB=torch.empty((n, 16), dtype=torch.float16, device=dev))
-        if len(_INT8_WS) > 8:
-            _INT8_WS.clear()
-        _INT8_WS[key] = ws
+    # workspace: ONE allocation per call from torch's caching allocator (stream-ordered reuse, safe across streams,
+    # threads and CUDA-graph capture -- a module-global scratch shared by every layer was a race); the flags, the
+    # counter and the index list must start at zero and sit together so that one small fill clears them
+    dev = A.device
+    idx_cap = max(k, 16)
+    sizes = [("colflag", k, torch.uint8), ("count", 1, torch.int32), ("idx", idx_cap, torch.int32), ("pos", k, torch.int16),
+             ("SCA", m, torch.float32), ("subA", m * 16, torch.float16), ("subB", n * 16, torch.float16), ("CA", m * k, torch.int8)]
+    offs, off = {}, 0
+    for name, cnt, dt in sizes:
+        offs[name] = off
+        off += (cnt * torch.empty((), dtype=dt).element_size() + 255) // 256 * 256
+    raw = torch.empty(off, dtype=torch.uint8, device=dev)
+    raw[:offs["pos"]].zero_()
+    ws = {name: raw[offs[name]:offs[name] + cnt * torch.empty((), dtype=dt).element_size()].view(dt) for name, cnt, dt in sizes}
+    ws["CA"] = ws["CA"].view(m, k)
+    ws["subA"] = ws["subA"].view(m, 16)
+    ws["subB"] = ws["subB"].view(n, 16)
     if bias is not None and bias.dtype != torch.float16:
         return None
     if out is None:

@@ -4,6 +4,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+#include <set>
+#include <utility>
+
 #include "../../include/bnb_b200.h"
 #include "common.cuh"
 
@@ -23,6 +27,17 @@ void latch_error(cudaError_t e, const char *where) {
   if (getenv("BNB_B200_VERBOSE")) fprintf(stderr, "bnb_b200 error: %s\n", tl_error_msg);
 }
 
+void ensure_max_dynamic_smem(const void *kernel, int bytes, const char *where) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void *>> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({dev, kernel})) return;
+  latch_error(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), where);
+  done.insert({dev, kernel});
+}
+
 // ---- typed entry points implemented in the kernel TUs -------------------------------------------
 template <typename T, int QT> void quantize_blockwise(const float *, const T *, float *, unsigned char *, int, long);
 template <typename T, int QT> void dequantize_blockwise(const float *, const unsigned char *, const float *, T *, int, long);
@@ -39,6 +54,7 @@ template <typename T> int gemm_4bit(int, int, int, const T *, const unsigned cha
 void get_col_row_stats(const __half *, float *, float *, int *, float, int, int);
 void double_rowcol_quant(const __half *, const float *, const float *, signed char *, signed char *, int *, int *, __half *, const int *, float, int, int);
 template <int FMT> void transform_row2fmt(const signed char *, signed char *, int, int, bool);
+void untransform_s8(int fmt, const signed char *A, signed char *out, int rows, int cols);
 template <int FMT> void extract_outliers(const signed char *, const int *, signed char *, int, int, int);
 void dequant_mm_int32_fp16(const int *, const float *, const float *, __half *, const __half *, int, int);
 int igemmlt(int, int, bool, int, int, int, const signed char *, const signed char *, void *, const float *, int, int, int);
@@ -137,6 +153,11 @@ void ctransform_row2turing(char *A, char *out, int rows, int cols) { transform_r
 void ctransform_row2turingT(char *A, char *out, int rows, int cols) { transform_row2fmt<COL_TURING>((signed char *)A, (signed char *)out, rows, cols, true); }
 void ctransform_row2ampere(char *A, char *out, int rows, int cols) { transform_row2fmt<COL_AMPERE>((signed char *)A, (signed char *)out, rows, cols, false); }
 void ctransform_row2ampereT(char *A, char *out, int rows, int cols) { transform_row2fmt<COL_AMPERE>((signed char *)A, (signed char *)out, rows, cols, true); }
+// inverse layouts: the reference's Python calls them (functional.py:2645-2647, maybe_rearrange_weight at checkpoint load)
+// although its own library never exported them (SURVEY 8a "WIP artefacts"); same argument convention as row2*
+void ctransform_turing2row(char *A, char *out, int rows, int cols) { untransform_s8(COL_TURING, (signed char *)A, (signed char *)out, rows, cols); }
+void ctransform_ampere2row(char *A, char *out, int rows, int cols) { untransform_s8(COL_AMPERE, (signed char *)A, (signed char *)out, rows, cols); }
+void ctransform_col322row(char *A, char *out, int rows, int cols) { untransform_s8(COL32, (signed char *)A, (signed char *)out, rows, cols); }
 
 int cigemmlt_turing_32(int m, int n, int k, const int8_t *A, const int8_t *B, void *C, float *row_scale, int lda, int ldb, int ldc) { return igemmlt(COL_TURING, 32, false, m, n, k, A, B, C, row_scale, lda, ldb, ldc); }
 int cigemmlt_turing_8(int m, int n, int k, const int8_t *A, const int8_t *B, void *C, float *row_scale, int lda, int ldb, int ldc) { return igemmlt(COL_TURING, 8, false, m, n, k, A, B, C, row_scale, lda, ldb, ldc); }
@@ -167,5 +188,11 @@ void *get_context(void) {
   cudaGetDevice(&c->device);
   return c;
 }
+// The reference loader sets .restype on these two unconditionally (python_src_quants/cextension.py:82-84), so an
+// UNMODIFIED loader needs the symbols to exist.  Neither is on the hot path (sparse handle: spmm; managed memory:
+// paged optimizers -- SURVEY 8b "out of scope"): both return NULL.  (The reference's own cget_managed_ptr returns an
+// uninitialised pointer, pythonInterface.cpp:380-387.)
+void *get_cusparse(void) { return nullptr; }
+void *cget_managed_ptr(size_t bytes) { (void)bytes; return nullptr; }
 
 }  // extern "C"

@@ -19,6 +19,8 @@ cudaStream_t current_stream();
 void set_current_stream(cudaStream_t s);
 void latch_error(cudaError_t e, const char *where);
 inline void check_launch(const char *where) { latch_error(cudaGetLastError(), where); }
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of on every launch (c_api.cu)
+void ensure_max_dynamic_smem(const void *kernel, int bytes, const char *where);
 
 // ---- 16-bit conversions (all round-to-nearest-even, one rounding)
 template <typename T> __device__ __forceinline__ float to_float(T v);

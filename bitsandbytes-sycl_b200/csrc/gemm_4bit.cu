@@ -27,6 +27,9 @@
 #include <stdlib.h>
 #include <type_traits>
 
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -259,19 +262,25 @@ __global__ void __launch_bounds__(256) k_gemm4_finalize(const float *__restrict_
   }
 }
 
-static float *g_ws[64] = {nullptr};
-static size_t g_ws_bytes[64] = {0};
+// split-K partial sums: one workspace per (device, stream) -- launches on one stream are ordered, two streams running
+// the kernel concurrently must not share it.  cudaFree of an outgrown buffer synchronises the device first.
+struct WsKey { int dev; cudaStream_t st; bool operator<(const WsKey &o) const { return dev != o.dev ? dev < o.dev : st < o.st; } };
+struct WsBuf { float *p; size_t bytes; };
+static std::mutex g_ws_mu;
+static std::map<WsKey, WsBuf> g_ws;
 
 static float *workspace(int dev, size_t bytes, cudaStream_t st) {
-  if (g_ws_bytes[dev] >= bytes) return g_ws[dev];
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  WsBuf &b = g_ws[WsKey{dev, st}];
+  if (b.bytes >= bytes) return b.p;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(st, &cs);
   if (cs != cudaStreamCaptureStatusNone) return nullptr;    // cannot grow inside a graph capture: caller falls back
-  if (g_ws[dev]) cudaFree(g_ws[dev]);
+  if (b.p) cudaFree(b.p);
   const size_t want = bytes < (size_t)(64u << 20) ? (size_t)(64u << 20) : bytes;
-  if (cudaMalloc(&g_ws[dev], want) != cudaSuccess) { g_ws[dev] = nullptr; g_ws_bytes[dev] = 0; cudaGetLastError(); return nullptr; }
-  g_ws_bytes[dev] = want;
-  return g_ws[dev];
+  if (cudaMalloc(&b.p, want) != cudaSuccess) { b.p = nullptr; b.bytes = 0; cudaGetLastError(); return nullptr; }
+  b.bytes = want;
+  return b.p;
 }
 }  // namespace g4
 
@@ -330,7 +339,7 @@ int gemm_4bit(int batch, int N, int K, const T *A, const unsigned char *B, const
   static bool attr_set[2][64] = {{false}};      // per element type AND per device
   const int ti = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
   if (!attr_set[ti][dev]) {
-    latch_error(cudaFuncSetAttribute(k_gemm4_tcgen05<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024), "gemm_4bit smem attr");
+    ensure_max_dynamic_smem(reinterpret_cast<const void *>(k_gemm4_tcgen05<T>), 226 * 1024, "gemm_4bit smem attr");
     attr_set[ti][dev] = true;
   }
   k_gemm4_tcgen05<T><<<dim3(tiles, a.splits), kThreads, smem, st>>>(tmX, tmW, a);

@@ -900,7 +900,6 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
 
 #undef BNB_MSEL
 #include "gemv_v2.cuh"
-#include "gemv_t.cuh"
 // ------------------------------------------------------------------------------------------------
 // TMA-staged block-column kernel (experiment, BNB_B200_GEMV_CFG=3x: measured equal to the register ring).
 //
@@ -1561,9 +1560,6 @@ static void launch_mma_inst(const GemvArgs &a) {
   }
   static int impl_v2 = -1;
   if (impl_v2 < 0) { const char *e = getenv("BNB_B200_GEMV_IMPL"); impl_v2 = (e && e[0] == '2') ? 1 : 0; }
-  static int impl_t = -1;
-  if (impl_t < 0) { const char *e = getenv("BNB_B200_GEMV_IMPL"); impl_t = (e && e[0] == 'T') ? 1 : 0; }
-  if (VEC4 && impl_t && a.batch == 1 && !exp_mode && launch_t<T, NESTED, false>(a2, ceil_div(a.N, 16), num_sms[dev])) return;
   if (VEC4 && impl_v2 && a.batch == 1 && !exp_mode && launch_v2<T, NESTED, false>(a2, ceil_div(a.N, 16), num_sms[dev])) return;
   if (VEC4 && impl_bc && a.batch == 1) {
     // block-column kernel, register ring.  Default: 8-warp CTAs, two per SM (<= 113 KB of shared memory and <= 128
@@ -1706,7 +1702,8 @@ static void next_hint(GemvArgs &a, const void *B, size_t bytes, const void *q, s
     if (g_pf_next.size() > 65536) g_pf_next.clear();
   }
   tl_prev_B = B;
-  if (h.B && h.B != B && h.bytes < (1ull << 31) && (reinterpret_cast<uintptr_t>(h.B) % 16) == 0 && device_range_ok(h.B, h.bytes)) {
+  // a next weight that would not stay in the 126 MB L2 next to the current one is not worth pulling early
+  if (h.B && h.B != B && h.bytes <= (size_t)(40u << 20) && bytes <= (size_t)(64u << 20) && (reinterpret_cast<uintptr_t>(h.B) % 16) == 0 && device_range_ok(h.B, h.bytes)) {
     a.pf_ptr[0] = static_cast<const unsigned char *>(h.B); a.pf_bytes[0] = (unsigned int)h.bytes;
     if (h.q && h.qbytes < (1ull << 31) && (reinterpret_cast<uintptr_t>(h.q) % 16) == 0 && device_range_ok(h.q, h.qbytes)) {
       a.pf_ptr[1] = static_cast<const unsigned char *>(h.q); a.pf_bytes[1] = (unsigned int)h.qbytes;
@@ -1715,8 +1712,18 @@ static void next_hint(GemvArgs &a, const void *B, size_t bytes, const void *q, s
 }
 
 // host copies of code[16] / code2[256] for the NEXT nested GEMV of this thread (consumed by that call)
-static thread_local const float *tl_code_host = nullptr, *tl_code2_host = nullptr;
-void set_gemv_host_tables(const float *code16, const float *code2_256) { tl_code_host = code16; tl_code2_host = code2_256; }
+static thread_local const float *tl_code_host = nullptr;
+void set_gemv_host_tables(const float *code16, const float *code2_256) { (void)code2_256; tl_code_host = code16; }
+// consumed (and cleared) at the very top of the next nested GEMV of this thread, whatever path that call then takes:
+// the pointer belongs to the caller and must not outlive the call
+static bool take_host_code_is_nf4() {
+  const float *c = tl_code_host;
+  tl_code_host = nullptr;
+  if (c == nullptr) return false;
+  static const float nf4[16] = BNB_NF4_TABLE;
+  for (int i = 0; i < 16; i++) if (c[i] != nf4[i]) return false;
+  return true;
+}
 
 template <typename T>
 void gemv_4bit_nested(int m, int n, int k, const T *A, const unsigned char *B, const unsigned char *qabsmax,
@@ -1724,6 +1731,7 @@ void gemv_4bit_nested(int m, int n, int k, const T *A, const unsigned char *B, c
                       int lda, int ldb, int ldc, int blocksize, int blocksize2, void *const *peer_outs, int npeers,
                       const GemvSync *sync) {
   (void)lda; (void)ldc;
+  const bool code_is_nf4 = take_host_code_is_nf4();
   if (m <= 0 || k <= 0) return;
   if (n < 1 || n > 8 || blocksize2 <= 0 || (blocksize2 & (blocksize2 - 1)) != 0 || !fast_path_ok(k, ldb, blocksize, A, B)) {
     latch_error(cudaErrorInvalidValue, "gemv_4bit_nested: needs 1<=n<=8, K%64==0, ldb==K/2, blocksize%64==0, aligned A/B");
@@ -1733,13 +1741,7 @@ void gemv_4bit_nested(int m, int n, int k, const T *A, const unsigned char *B, c
   a.N = m; a.K = k; a.batch = n; a.blocksize = blocksize;
   a.x = A; a.B = B; a.qabsmax = qabsmax; a.absmax2 = absmax2; a.code2 = code2; a.offset = offset;
   a.code = datatype; a.out = out;
-  if (tl_code_host != nullptr) {
-    static const float nf4[16] = BNB_NF4_TABLE;
-    bool same = true;
-    for (int i = 0; i < 16; i++) same = same && (tl_code_host[i] == nf4[i]);
-    if (same) a.tables_in_args = 2;
-  }
-  tl_code_host = tl_code2_host = nullptr;
+  if (code_is_nf4) a.tables_in_args = 2;
   if (npeers > 0) {
     // peer stores exist only in the block-column kernel (batch 1, blocksize 64, K % 256 == 0, K small enough for shared memory)
     if (npeers > 7 || n != 1 || blocksize != 64 || (k % 256) != 0 || k > 28672 || !peer_outs) {
@@ -1767,6 +1769,7 @@ int gemv_4bit_nested_multi(int count, const int *ms, int k, const T *A, const un
                            const unsigned char *const *qabs, const float *const *am2s, const float *code2,
                            const float *offsets, const float *datatype, T *const *outs, int blocksize, int blocksize2,
                            void *const *peer_outs, int npeers) {
+  const bool code_is_nf4 = take_host_code_is_nf4();
   if (npeers < 0 || npeers > 7 || (npeers > 0 && peer_outs == nullptr)) return 1;
   if (count < 1 || count > 4 || k <= 0 || blocksize != 64 || (k % 256) != 0 || blocksize2 <= 0 || (blocksize2 & (blocksize2 - 1)) != 0 ||
       (reinterpret_cast<uintptr_t>(A) % 16) != 0)
@@ -1787,13 +1790,7 @@ int gemv_4bit_nested_multi(int count, const int *ms, int k, const T *A, const un
   for (int i = 0; i < count; i++)
     for (int p = 0; p < npeers; p++) a.mpeer[i][p] = peer_outs[i * npeers + p];     // matrix-major
   a.N = nsum; a.B = Bs[0]; a.qabsmax = qabs[0]; a.absmax2 = am2s[0]; a.offset = offsets[0]; a.out = outs[0];
-  if (tl_code_host != nullptr) {
-    static const float nf4[16] = BNB_NF4_TABLE;
-    bool same = true;
-    for (int i = 0; i < 16; i++) same = same && (tl_code_host[i] == nf4[i]);
-    if (same) a.tables_in_args = 2;
-  }
-  tl_code_host = tl_code2_host = nullptr;
+  if (code_is_nf4) a.tables_in_args = 2;
   int dev = 0, sms = kNumSMs;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1804,9 +1801,6 @@ int gemv_4bit_nested_multi(int count, const int *ms, int k, const T *A, const un
   {
     static int impl_v2 = -1;
     if (impl_v2 < 0) { const char *e = getenv("BNB_B200_GEMV_IMPL"); impl_v2 = (e && e[0] == '2') ? 1 : 0; }
-    static int impl_t = -1;
-    if (impl_t < 0) { const char *e = getenv("BNB_B200_GEMV_IMPL"); impl_t = (e && e[0] == 'T') ? 1 : 0; }
-    if (impl_t && launch_t<T, true, true>(a, tiles, sms)) return 0;
     if (impl_v2 && launch_v2<T, true, true>(a, tiles, sms)) return 0;
   }
   int warps = 8, grid = tiles < sms * 2 ? tiles : sms * 2;

@@ -18,6 +18,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -89,11 +92,13 @@ constexpr int kTmemCols = 512;
 constexpr int kIgemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * (4 + 4) /*col stats + bias (fp32)*/ +
                            2 * BN * 8 * 4 /*outlier columns of the weight as fp32, per accumulator buffer*/;
 
-enum { EPI_INT32 = 0, EPI_DEQUANT_FP16 = 1 };
+enum { EPI_INT32 = 0, EPI_DEQUANT_FP16 = 1, EPI_INT32_COL32 = 2, EPI_S8_COL32 = 3 };   // the last two: the reference ABI's C layout, written by the epilogue
 
 struct IgemmArgs {
   int M, N, K;
-  int *C;                  // EPI_INT32: row-major [M,N]
+  int *C;                  // EPI_INT32: row-major [M,N]; EPI_INT32_COL32: col32 [ceil(N/32)][M][32]
+  signed char *C8;         // EPI_S8_COL32: col32 int8, saturated rint(acc * alpha)
+  const float *row_scale;  // EPI_S8_COL32: per-row alpha (null: 1.0f)
   const float *rowStats;   // EPI_DEQUANT_FP16
   const float *colStats;
   const __half *bias;      // may be null
@@ -237,7 +242,42 @@ k_igemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int cl = half_n * (BN / 2) + c * 32;   // column inside the tile
         const int col0 = n_blk * BN + cl;
         if (row < a.M && col0 < a.N) {
-          if (EPI == EPI_INT32) {
+          if (EPI == EPI_INT32_COL32) {
+            // col32 (blas_utils.h:263-266): element (r, c) at (c/32)*32*M + r*32 + c%32 -- the 32 columns this thread holds
+            // are one contiguous 128-byte run; the padding columns of the last panel are left as the caller zeroed them
+            int *dst = a.C + ((size_t)(col0 >> 5) * a.M + row) * 32;
+            if (col0 + 32 <= a.N) {
+#pragma unroll
+              for (int j = 0; j < 8; j++)
+                reinterpret_cast<int4 *>(dst)[j] = make_int4((int)v[4 * j], (int)v[4 * j + 1], (int)v[4 * j + 2], (int)v[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (col0 + j < a.N) dst[j] = (int)v[j];
+            }
+          } else if (EPI == EPI_S8_COL32) {
+            const float alpha = a.row_scale != nullptr ? a.row_scale[row] : 1.0f;
+            signed char *dst = a.C8 + ((size_t)(col0 >> 5) * a.M + row) * 32;
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              uint32_t w4 = 0;
+#pragma unroll
+              for (int b = 0; b < 4; b++) {
+                const int q8 = max(-128, min(127, __float2int_rn(__fmul_rn(__int2float_rn((int)v[4 * j + b]), alpha))));
+                w4 |= (uint32_t)(q8 & 0xFF) << (8 * b);
+              }
+              pk[j] = w4;
+            }
+            if (col0 + 32 <= a.N) {
+              reinterpret_cast<uint4 *>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              reinterpret_cast<uint4 *>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (col0 + j < a.N) dst[j] = (signed char)((pk[j >> 2] >> (8 * (j & 3))) & 0xFF);
+            }
+          } else if (EPI == EPI_INT32) {
             int *dst = a.C + (long)row * a.N + col0;
             if (col0 + 32 <= a.N && (a.N & 3) == 0) {
 #pragma unroll
@@ -349,7 +389,12 @@ __global__ void __launch_bounds__(256) k_igemm_simt(const signed char *__restric
       const int r = m0 + ty * 4 + i, c = n0 + tx * 4 + j;
       if (r < a.M && c < a.N) {
         if (EPI == EPI_INT32) a.C[(long)r * a.N + c] = acc[i][j];
-        else {
+        else if (EPI == EPI_INT32_COL32) a.C[((size_t)(c >> 5) * a.M + r) * 32 + (c & 31)] = acc[i][j];
+        else if (EPI == EPI_S8_COL32) {
+          const float alpha = a.row_scale != nullptr ? a.row_scale[r] : 1.0f;
+          a.C8[((size_t)(c >> 5) * a.M + r) * 32 + (c & 31)] =
+              (signed char)max(-128, min(127, __float2int_rn(__fmul_rn(__int2float_rn(acc[i][j]), alpha))));
+        } else {
           float t = __fmul_rn(__int2float_rn(acc[i][j]), 6.200012e-05f);
           t = __fmul_rn(t, a.rowStats[r]);
           t = __fmul_rn(t, a.colStats[c]);
@@ -381,7 +426,7 @@ static int igemm_rowmajor(const signed char *A, const signed char *B, const Igem
     cudaGetDevice(&dev);
     static bool attr_set[64] = {false};          // the attribute is per device: one process may drive several GPUs
     if (!attr_set[dev & 63]) {
-      latch_error(cudaFuncSetAttribute(k_igemm_tcgen05<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIgemmSmem), "igemm smem attr");
+      ensure_max_dynamic_smem(reinterpret_cast<const void *>(k_igemm_tcgen05<EPI>), kIgemmSmem, "igemm smem attr");
       attr_set[dev & 63] = true;
     }
     const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
@@ -415,22 +460,40 @@ int igemm_rowmajor_dequant_outliers_fp16(int m, int n, int k, const signed char 
   IgemmArgs a{};
   a.M = m; a.N = n; a.K = k; a.rowStats = rowStats; a.colStats = colStats; a.bias = bias; a.out = out;
   a.subA = subA; a.subB = subB; a.nout = count;
-  if ((k % 16) != 0 || (reinterpret_cast<uintptr_t>(A) % 16) != 0 || (reinterpret_cast<uintptr_t>(B) % 16) != 0) return 1;  // tcgen05 path only
+  // the outlier term exists in the tcgen05 epilogue only: refuse (caller takes the step-by-step route) whenever the SIMT
+  // kernel would run, including when it is forced for debugging
+  if ((k % 16) != 0 || (reinterpret_cast<uintptr_t>(A) % 16) != 0 || (reinterpret_cast<uintptr_t>(B) % 16) != 0 || env_force_simt()) return 1;
   return igemm_rowmajor<EPI_DEQUANT_FP16>(A, B, a);
 }
 
 // ------------------------------------------------------------------------------------------------
 // reference ABI: A col32, B col_turing / col_ampere, C col32 (int32, or saturated int8 with fp32 alpha)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_scale_to_s8(const int *__restrict__ C, signed char *__restrict__ out, const float *__restrict__ row_scale,
-                              int m, int n) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long)m * n) return;
-  const float alpha = row_scale ? row_scale[i / n] : 1.0f;
-  const int q = __float2int_rn(__fmul_rn(__int2float_rn(C[i]), alpha));
-  out[i] = (signed char)max(-128, min(127, q));
+// scratch for the un-permuted operands: one buffer per (device, stream), grown on demand (launches on a stream are
+// ordered, so consecutive calls may reuse it; cudaFree of an outgrown buffer synchronises the device first)
+struct LtKey { int dev; cudaStream_t st; bool operator<(const LtKey &o) const { return dev != o.dev ? dev < o.dev : st < o.st; } };
+struct LtBuf { signed char *p; size_t bytes; };
+static std::mutex g_lt_mu;
+static std::map<LtKey, LtBuf> g_lt;
+static signed char *lt_scratch(size_t bytes, cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_lt_mu);
+  LtBuf &b = g_lt[LtKey{dev, st}];
+  if (b.bytes >= bytes) return b.p;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  if (cs != cudaStreamCaptureStatusNone) return nullptr;    // cannot grow inside a graph capture
+  if (b.p) cudaFree(b.p);
+  if (cudaMalloc(&b.p, bytes) != cudaSuccess) { b.p = nullptr; b.bytes = 0; cudaGetLastError(); return nullptr; }
+  b.bytes = bytes;
+  return b.p;
 }
 
+// cigemmlt_<fmt>_<32|8|8_rowscale> (reference op_gemm.cpp:541-638): A col32, B col_turing / col_ampere, C col32.
+// The tensor-core kernel wants K-major rows for TMA, so the two int8 operands are un-permuted into per-stream scratch
+// (17 + 67 MB for config 3: ~10 % of the GEMM's time); C is written in col32 -- int32, or int8 saturated from
+// rint(acc * alpha) -- straight from the epilogue: no int32 round trip through a third buffer, no allocation per call.
 int igemmlt(int fmtB, int dtype_out, bool scale_rows, int m, int n, int k, const signed char *A, const signed char *B,
             void *C, const float *row_scale, int lda, int ldb, int ldc) {
   if (m <= 0 || n <= 0) return 0;
@@ -438,33 +501,21 @@ int igemmlt(int fmtB, int dtype_out, bool scale_rows, int m, int n, int k, const
   (void)ldb;
   if (scale_rows && row_scale == nullptr) return 2;
   cudaStream_t st = current_stream();
-  signed char *Arm = nullptr, *Brm = nullptr, *C8 = nullptr;
-  int *Crm = nullptr;
-  const size_t szA = (size_t)m * k, szB = (size_t)n * k, szC = (size_t)m * n * sizeof(int);
-  if (cudaMallocAsync(&Arm, szA, st) != cudaSuccess || cudaMallocAsync(&Brm, szB, st) != cudaSuccess ||
-      cudaMallocAsync(&Crm, szC, st) != cudaSuccess) {
-    latch_error(cudaGetLastError(), "igemmlt scratch");
-    return 2;
-  }
+  const size_t szA = ((size_t)m * k + 255) & ~(size_t)255, szB = ((size_t)n * k + 255) & ~(size_t)255;
+  signed char *scratch = lt_scratch(szA + szB, st);
+  if (scratch == nullptr) { latch_error(cudaErrorMemoryAllocation, "igemmlt scratch"); return 2; }
+  signed char *Arm = scratch, *Brm = scratch + szA;
   untransform_s8(COL32, A, Arm, m, k);
   untransform_s8(fmtB, B, Brm, n, k);
-  int rc = igemm_rowmajor_32(m, n, k, Arm, Brm, Crm);
-  if (rc == 0) {
-    if (dtype_out == 32) {
-      to_col32<int>(Crm, reinterpret_cast<int *>(C), m, n);
-    } else {
-      if (cudaMallocAsync(&C8, (size_t)m * n, st) != cudaSuccess) rc = 2;
-      else {
-        k_scale_to_s8<<<(unsigned)ceil_div_ll((long)m * n, 256), 256, 0, st>>>(Crm, C8, scale_rows ? row_scale : nullptr, m, n);
-        to_col32<signed char>(C8, reinterpret_cast<signed char *>(C), m, n);
-        cudaFreeAsync(C8, st);
-      }
-    }
+  IgemmArgs a{};
+  a.M = m; a.N = n; a.K = k;
+  if (dtype_out == 32) {
+    a.C = reinterpret_cast<int *>(C);
+    return igemm_rowmajor<EPI_INT32_COL32>(Arm, Brm, a);
   }
-  cudaFreeAsync(Arm, st);
-  cudaFreeAsync(Brm, st);
-  cudaFreeAsync(Crm, st);
-  return rc;
+  a.C8 = reinterpret_cast<signed char *>(C);
+  a.row_scale = scale_rows ? row_scale : nullptr;
+  return igemm_rowmajor<EPI_S8_COL32>(Arm, Brm, a);
 }
 
 }  // namespace bnb

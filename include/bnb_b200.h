@@ -23,6 +23,7 @@
 #ifndef BNB_B200_H
 #define BNB_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -79,6 +80,12 @@ BNB_B200_API void ctransform_row2turing(char *A, char *out, int rows, int cols);
 BNB_B200_API void ctransform_row2turingT(char *A, char *out, int rows, int cols);
 BNB_B200_API void ctransform_row2ampere(char *A, char *out, int rows, int cols);
 BNB_B200_API void ctransform_row2ampereT(char *A, char *out, int rows, int cols);
+/* inverse layouts -> row-major.  python_src_quants/functional.py:2645-2647 calls ctransform_turing2row / ctransform_ampere2row
+ * (checkpoint load: nn/modules.py:635-654 maybe_rearrange_weight); the reference library itself never exported them.
+ * out is [rows, cols] row-major int8; A holds the padded layout of a [rows, cols] matrix (blas_utils.h:244-346). */
+BNB_B200_API void ctransform_turing2row(char *A, char *out, int rows, int cols);
+BNB_B200_API void ctransform_ampere2row(char *A, char *out, int rows, int cols);
+BNB_B200_API void ctransform_col322row(char *A, char *out, int rows, int cols);
 
 /* --- int8 GEMM C = A * B^T: sycl/pythonInterface.cpp:298-316 (igemmlt, op_gemm.cpp:541-655).
  * A: int8 col32 [m,k] (lda = m*32); B: int8 col_turing / col_ampere [n,k]; C: col32 [m,n] (ldc = m*32),
@@ -101,6 +108,13 @@ BNB_B200_API void cextractOutliers_ampere(char *A, int *idx, char *out, int idx_
 /* --- context: sycl/pythonInterface.cpp:295; presence of this symbol marks the library GPU-capable
  * (python_src_quants/cextension.py:103). Returns a leaked opaque handle, as the reference does. */
 BNB_B200_API void *get_context(void);
+/* touched by the reference loader only (python_src_quants/cextension.py:82-84 sets their restype unconditionally):
+ * sycl/pythonInterface.cpp:296 and :380-387.  Off the hot path (spmm handle / managed memory): both return NULL. */
+BNB_B200_API void *get_cusparse(void);
+BNB_B200_API void *cget_managed_ptr(size_t bytes);
+/* NOT exported on purpose: cquantize_blockwise_cpu_fp32 / cdequantize_blockwise_cpu_fp32 (sycl/pythonInterface.cpp:419-420,
+ * SURVEY 8b).  They are the reference's CPU fallback; this library has no CPU path (the Python layer raises for CPU
+ * tensors), and the reference's CPU implementation lives on as test infrastructure only (oracle/_ref). */
 
 /* ============================== 2. additive symbols (this library only) ============================== */
 

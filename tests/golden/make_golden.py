@@ -201,8 +201,62 @@ def device_trees():
     print("device tree fixtures:", {k: (v.shape, v.dtype) for k, v in out.items()}, "bytes", os.path.getsize(os.path.join(HERE, "ref_device_trees.npz")))
 
 
+def loader_and_call_sites():
+    """ref_abi_call_sites.json: every `lib.<symbol>` the reference's hot-path Python functions call
+    (python_src_quants/functional.py) and every attribute the reference LOADER touches on the CDLL
+    (python_src_quants/cextension.py:79-85, 103) -- what an unmodified reference needs from a replacement .so."""
+    src = open(os.path.join(REF, "python_src_quants/functional.py")).read()
+    hot = {"quantize_blockwise", "dequantize_blockwise", "quantize_4bit", "dequantize_4bit", "gemv_4bit", "get_colrow_absmax",
+           "double_quant", "transform", "igemmlt", "mm_dequant", "extract_outliers"}
+    calls = {}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name in hot:
+            calls[node.name] = sorted(set(re.findall(r"\blib\.(\w+)", ast.get_source_segment(src, node))))
+    lsrc = open(os.path.join(REF, "python_src_quants/cextension.py")).read()
+    loader = sorted(set(re.findall(r"\blib\.(\w+)\.restype", lsrc)) | set(re.findall(r'hasattr\(dll, "(\w+)"\)', lsrc)))
+    json.dump({"functional_call_sites": calls, "loader_attributes": loader,
+               "source": ["python_src_quants/functional.py", "python_src_quants/cextension.py"]},
+              open(os.path.join(HERE, "ref_abi_call_sites.json"), "w"), indent=1)
+    print("loader touches:", loader)
+
+
+def checkpoint_fixture():
+    """ref_quantstate_packed.npz: a nested NF4 QuantState serialised by the REFERENCE's own QuantState.as_dict(packed=True)
+    (python_src_quants/functional.py:625-798, class cut out with ast; pack_dict_to_tensor from utils.py:169-183) -- the
+    wire format of Linear4bit._save_to_state_dict (nn/modules.py:436-445)."""
+    fsrc = open(os.path.join(REF, "python_src_quants/functional.py")).read()
+    usrc = open(os.path.join(REF, "python_src_quants/utils.py")).read()
+    ns = {"torch": torch, "Tensor": torch.Tensor, "Dict": __import__("typing").Dict, "Any": __import__("typing").Any, "json": json}
+    for node in ast.parse(usrc).body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("pack_dict_to_tensor", "unpack_tensor_to_dict"):
+            exec(ast.get_source_segment(usrc, node), ns)
+    for node in ast.parse(fsrc).body:
+        if isinstance(node, ast.ClassDef) and node.name == "QuantState":
+            exec(ast.get_source_segment(fsrc, node), ns)
+    QS = ns["QuantState"]
+    tables = np.load(os.path.join(HERE, "ref_python_tables.npz"))
+    g = torch.Generator().manual_seed(77)
+    N, K = 64, 256
+    nblocks = N * K // 64
+    s2 = QS(absmax=torch.rand(nblocks // 256, generator=g) * 0.01 + 0.001, blocksize=256, code=torch.from_numpy(tables["dynamic_map"].copy()),
+            dtype=torch.float32)
+    st = QS(absmax=torch.randint(0, 256, (nblocks,), generator=g, dtype=torch.uint8), shape=torch.Size((N, K)),
+            code=torch.from_numpy(tables["nf4"].copy()), blocksize=64, quant_type="nf4", dtype=torch.bfloat16,
+            offset=torch.tensor(0.017303466796875), state2=s2)
+    packed = st.as_dict(packed=True)
+    out = {k: v.numpy() for k, v in packed.items()}
+    out["weight"] = torch.randint(0, 256, (N * K // 2, 1), generator=g, dtype=torch.uint8).numpy()
+    np.savez_compressed(os.path.join(HERE, "ref_quantstate_packed.npz"), **out)
+    # round trip through the reference's own from_dict as a self-check
+    back = QS.from_dict({k: v.clone() for k, v in packed.items()}, device=torch.device("cpu"))
+    assert back == st and back.offset.item() == st.offset.item()
+    print("quantstate fixture keys:", sorted(out))
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run this where /root/reference exists"
+    checkpoint_fixture()
+    loader_and_call_sites()
     python_tables()
     kernel_constants()
     cpu_blockwise()

@@ -121,3 +121,61 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(d, f)).read()
                 assert "oracle" not in txt.replace("# oracle", ""), os.path.join(d, f)
+
+
+def test_unmodified_reference_loader_and_call_sites_bind():
+    """tests/golden/ref_abi_call_sites.json (cut out of the reference by make_golden.py) lists what the reference's own
+    loader touches on the CDLL (cextension.py:79-85: restype of get_context / get_cusparse / cget_managed_ptr, and
+    hasattr(get_context) at :103) and every lib.<symbol> its hot-path functions call.  Replay both against the .so:
+    the loader sequence must not raise, and every call site except the two CPU-fallback symbols must resolve."""
+    from bnb_b200.cextension import LIB_PATH
+    g = json.load(open(os.path.join(GOLDEN, "ref_abi_call_sites.json")))
+    dll = ct.cdll.LoadLibrary(LIB_PATH)
+    assert hasattr(dll, "get_context")                      # "only a CUDA-built library exposes this"
+    for name in g["loader_attributes"]:                     # SYCLBNBNativeLibrary.__init__
+        getattr(dll, name).restype = ct.c_void_p
+    assert set(g["loader_attributes"]) >= {"get_context", "get_cusparse", "cget_managed_ptr"}
+    cpu_only = {"cquantize_blockwise_cpu_fp32", "cdequantize_blockwise_cpu_fp32"}   # no CPU path here, by design (header note)
+    missing = sorted({s for fn, syms in g["functional_call_sites"].items() for s in syms if s not in cpu_only and not hasattr(dll, s)})
+    assert not missing, missing
+    dll.get_cusparse.restype = ct.c_void_p
+    dll.cget_managed_ptr.restype = ct.c_void_p
+    dll.cget_managed_ptr.argtypes = [ct.c_size_t]
+    assert dll.get_cusparse() is None and dll.cget_managed_ptr(64) is None       # off the hot path: NULL, no allocation
+
+
+def test_quantstate_wire_format_matches_reference_serialisation():
+    """tests/golden/ref_quantstate_packed.npz was written by the reference's OWN QuantState.as_dict(packed=True)
+    (functional.py:686-767, class executed from the reference source by make_golden.py).  This repo's QuantState must
+    read it (from_dict) and write the same bytes back (as_dict) -- tensors and the JSON blob of the non-tensor items."""
+    from bnb_b200.functional import QuantState
+    g = np.load(os.path.join(GOLDEN, "ref_quantstate_packed.npz"))
+    ref = {k: torch.from_numpy(g[k].copy()) for k in g.files if k != "weight"}
+    st = QuantState.from_dict({k: v.clone() for k, v in ref.items()}, device=torch.device("cpu"))
+    assert st.nested and st.quant_type == "nf4" and st.blocksize == 64 and st.dtype == torch.bfloat16
+    assert tuple(st.shape) == (64, 256) and st.state2.blocksize == 256 and st.state2.dtype == torch.float32
+    assert st.absmax.dtype == torch.uint8 and torch.equal(st.absmax, ref["absmax"])
+    assert torch.equal(st.state2.absmax, ref["nested_absmax"]) and torch.equal(st.state2.code, ref["nested_quant_map"])
+    assert torch.equal(st.code, ref["quant_map"]) and float(st.offset) == 0.017303466796875
+    mine = st.as_dict(packed=True)
+    assert sorted(mine) == sorted(ref)
+    for k in ref:
+        assert torch.equal(mine[k], ref[k]), k          # byte-identical, including the packed JSON
+
+
+@pytest.mark.parametrize("fmt", ["col32", "col_turing", "col_ampere"])
+@pytest.mark.parametrize("shape", [(64, 64), (40, 96), (129, 160)])
+def test_undo_layout_to_row_inverts_the_reference_layouts(fmt, shape):
+    """Checkpoint load path (reference nn/modules.py:635-654 maybe_rearrange_weight -> undo_layout): the host-side inverse
+    of col32 / col_turing / col_ampere against the oracle's forward maps (kernel_quant.cpp:3673-3832)."""
+    from bnb_b200 import functional as F
+    from oracle import oracle as orc
+    rows, cols = shape
+    rng = np.random.RandomState(rows + cols)
+    A = rng.randint(-128, 128, (rows, cols)).astype(np.int8)
+    buf = orc.transform(A, fmt)
+    pr = {"col32": rows, "col_turing": (rows + 7) // 8 * 8, "col_ampere": (rows + 31) // 32 * 32}[fmt]
+    pc = (cols + 31) // 32 * 32
+    assert buf.size == pr * pc
+    back = F.undo_layout_to_row(torch.from_numpy(buf.reshape(pr, pc)), fmt, rows, cols)
+    assert np.array_equal(back.numpy(), A)

@@ -61,7 +61,7 @@ def test_gemm_4bit_vs_fp64(F, batch, N, K, dtype, nested, blocksize, with_bias):
     x = torch.randn(batch, K).to(DT[dtype])
     bias = (torch.randn(N) * 0.1).to(DT[dtype]).cuda() if with_bias else None
     q, st = F.quantize_4bit(W.cuda(), blocksize=blocksize, compress_statistics=nested, quant_type="nf4")
-    y = F.gemm_4bit(x.cuda(), q, st, bias=bias)
+    y = F.gemm_4bit(x.cuda(), q.t(), st, bias=bias)
     assert y is not None, "fused kernel refused a supported shape"
     assert y.shape == (batch, N) and y.dtype == DT[dtype]
     y64 = reference64(F, x, q, st, dtype, bias)
@@ -96,7 +96,7 @@ def test_gemm_4bit_refuses_what_it_cannot_do(F):
     W = (torch.randn(64, 96) * 0.02).bfloat16()
     q, st = F.quantize_4bit(W.cuda(), blocksize=64, quant_type="nf4")      # numel 6144 = 96 blocks
     x = torch.randn(8, 96).bfloat16().cuda()
-    assert F.gemm_4bit(x, q, st) is None
+    assert F.gemm_4bit(x, q.t(), st) is None
     import bnb_b200
     y = bnb_b200.matmul_4bit(x, q.t(), quant_state=st)
     assert y.shape == (8, 64) and torch.isfinite(y).all()
@@ -167,7 +167,7 @@ def test_small_batch_rides_the_gemv_kernels(F, batch, N, K, dtype, with_bias):
     x = torch.randn(batch, K).to(DT[dtype]).cuda()
     bias = torch.randn(N).to(DT[dtype]).cuda() if with_bias else None
     q, st = F.quantize_4bit(W, blocksize=64, compress_statistics=True, quant_type="nf4")
-    y = F.gemm_4bit(x, q, st, bias=bias)
+    y = F.gemm_4bit(x, q.t(), st, bias=bias)
     assert y is not None and y.shape == (batch, N) and y.dtype == DT[dtype]
     st32 = copy.copy(st)
     st32.dtype = torch.float32
@@ -180,3 +180,22 @@ def test_small_batch_rides_the_gemv_kernels(F, batch, N, K, dtype, with_bias):
     for b in range(batch):
         err = float((y[b].double() - ref[b]).norm() / ref[b].norm())
         assert err <= tol, (b, err)
+
+
+def test_gemm_4bit_shape_checks_follow_the_reference(F):
+    """The reference's batch>1 route is F.linear(A, dequantize_4bit(B, state).t()): a wrong activation width raises a
+    shape error there, and an un-transposed packed weight computes A @ W.  The fused kernel must not silently read
+    out of bounds or compute the other product: it refuses, and the reference-shaped route decides."""
+    import bnb_b200
+    torch.manual_seed(1)
+    W = (torch.randn(128, 256) * 0.02).bfloat16()
+    q, st = F.quantize_4bit(W.cuda(), blocksize=64, quant_type="nf4")
+    x_bad = torch.randn(16, 192, device="cuda").bfloat16()
+    assert F.gemm_4bit(x_bad, q.t(), st) is None
+    with pytest.raises(RuntimeError):
+        bnb_b200.matmul_4bit(x_bad, q.t(), quant_state=st)
+    x_n = torch.randn(16, 128, device="cuda").bfloat16()          # A @ W (un-transposed B): [16,128] @ [128,256]
+    assert F.gemm_4bit(x_n, q, st) is None
+    y = bnb_b200.matmul_4bit(x_n, q, quant_state=st)
+    ref = x_n.float() @ F.dequantize_4bit(q, st).float()
+    assert y.shape == (16, 256) and (y.float() - ref).abs().max().item() <= 2.0 ** -6 * ref.abs().max().item()

@@ -464,3 +464,47 @@ def test_int8_linear_fused_config3_paths_vs_oracle(F, k, m, n_outlier_cols):
         d = np.abs(yk.astype(np.float32) - y_o.astype(np.float32))
         assert (d <= 2.01 * ulp).all(), float((d / ulp).max())
         assert (d > 0).mean() < 0.02
+
+
+@pytest.mark.parametrize("fmt", ["col32", "col_turing", "col_ampere"])
+@pytest.mark.parametrize("shape", [(64, 64), (37, 300), (512, 4096)])
+def test_inverse_layout_transforms(F, fmt, shape):
+    """ctransform_{col32,turing,ampere}2row (the reference's Python calls the last two at functional.py:2645-2647):
+    row -> layout -> row is the identity, and the device inverse agrees with the host-side undo_layout_to_row."""
+    rows, cols = shape
+    rng = np.random.RandomState(rows * 7 + cols)
+    A = torch.from_numpy(rng.randint(-128, 128, (rows, cols)).astype(np.int8)).cuda()
+    buf, S = F.transform(A, fmt)
+    back, S2 = F.transform(buf, "row", state=S)
+    assert S2[1] == "row" and back.shape == (rows, cols)
+    assert torch.equal(back, A)
+    host = F.undo_layout_to_row(buf.cpu(), fmt, rows, cols)
+    assert torch.equal(host, A.cpu())
+    assert np.array_equal(buf.cpu().numpy().ravel(), orc.transform(A.cpu().numpy(), fmt))
+
+
+@pytest.mark.parametrize("fmt", ["col_turing", "col_ampere"])
+def test_linear8bitlt_loads_reference_format_checkpoint(F, fmt):
+    """A state dict as upstream bitsandbytes / the reference writes it from `state.CxB` (nn/modules.py:725-796): int8
+    weight in col_turing / col_ampere + `weight_format` code + SCB.  maybe_rearrange_weight (:635-654) must bring it
+    back to row-major at load time; the loaded layer computes exactly what the row-format layer computes."""
+    import bnb_b200
+    from bnb_b200.utils import LINEAR_8BIT_WEIGHTS_FORMAT_MAPPING
+    torch.manual_seed(21)
+    k, n = 256, 96 if fmt == "col_turing" else 128       # whole 8- / 32-row tiles, as undo_layout requires
+    lin = bnb_b200.nn.Linear8bitLt(k, n, bias=True, has_fp16_weights=False, threshold=6.0).cuda().half()
+    x = torch.randn(24, k, device="cuda").half()
+    x[:, 5] = 7.0
+    with torch.no_grad():
+        y0 = lin(x)
+    sd = lin.state_dict()
+    CB = sd["weight"]
+    assert CB.dtype == torch.int8 and CB.shape == (n, k)
+    CxB, _ = F.transform(CB.cuda(), fmt)
+    sd_ref = {"weight": CxB.cpu(), "bias": sd["bias"].cpu(), "SCB": sd["SCB"].cpu(),
+              "weight_format": torch.tensor(LINEAR_8BIT_WEIGHTS_FORMAT_MAPPING[fmt], dtype=torch.uint8)}
+    lin2 = bnb_b200.nn.Linear8bitLt(k, n, bias=True, has_fp16_weights=False, threshold=6.0).cuda().half()
+    lin2.load_state_dict(sd_ref)
+    with torch.no_grad():
+        y1 = lin2(x)
+    assert torch.equal(y0, y1)

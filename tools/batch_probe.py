@@ -30,10 +30,10 @@ def run(N,K,n,dt=torch.bfloat16):
     e1.record(); torch.cuda.synchronize()
     us=e0.elapsed_time(e1)*1e3/50
     # K4 for comparison
-    y=F.gemm_4bit(x,q,st); torch.cuda.synchronize()
+    y=F.gemm_4bit(x,q.t(),st); torch.cuda.synchronize()
     g2=torch.cuda.CUDAGraph()
     with torch.cuda.graph(g2):
-        for _ in range(10): F.gemm_4bit(x,q,st)
+        for _ in range(10): F.gemm_4bit(x,q.t(),st)
     g2.replay(); torch.cuda.synchronize()
     e0.record()
     for _ in range(5): g2.replay()

@@ -138,8 +138,8 @@ def bench_gemm4(iters):
         for batch in (16, 32, 64, 128, 256):
             x = torch.randn(batch, K, device="cuda").bfloat16()
             outs = [torch.empty(batch, N, dtype=torch.bfloat16, device="cuda") for _ in range(nbuf)]
-            F.gemm_4bit(x, qs[0], st, out=outs[0])   # allocates the split-K workspace outside the capture
-            fns = [(lambda i=i: F.gemm_4bit(x, qs[i], st, out=outs[i])) for i in range(nbuf)]
+            F.gemm_4bit(x, qs[0].t(), st, out=outs[0])   # allocates the split-K workspace outside the capture
+            fns = [(lambda i=i: F.gemm_4bit(x, qs[i].t(), st, out=outs[i])) for i in range(nbuf)]
             us = time_graph(fns, iters)
             nbytes = N * K // 2 + 4 * N * K // 64 + 2 * batch * (K + N)
             flops = 2.0 * batch * N * K

@@ -35,7 +35,7 @@ elif what == "gemm4":
     packs = [q.clone() for _ in range(4)]
     x = torch.randn(batch, K, device="cuda").bfloat16()
     for i in range(8):
-        y = F.gemm_4bit(x, packs[i % 4], st)
+        y = F.gemm_4bit(x, packs[i % 4].t(), st)
 elif what == "stats":
     A = [torch.randn(4096, 4096, device="cuda").half() for _ in range(4)]
     for i in range(8):
