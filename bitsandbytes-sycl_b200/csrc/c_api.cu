@@ -43,6 +43,7 @@ template <typename T, int QT> void quantize_blockwise(const float *, const T *, 
 template <typename T, int QT> void dequantize_blockwise(const float *, const unsigned char *, const float *, T *, int, long);
 long long selftest_quant_lut(int qtype);
 void gemv_probe(unsigned long long *out2);
+void gemv_trace(unsigned long long *out);
 void set_gemv_host_tables(const float *code16, const float *code2_256);
 template <typename T> int gemv_4bit_nested_multi(int, const int *, int, const T *, const unsigned char *const *, const unsigned char *const *, const float *const *, const float *, const float *, const float *, T *const *, int, int, void *const *, int);
 template <typename T> void gemv_4bit(int, int, int, const T *, const unsigned char *, const float *, const float *, T *, int, int, int, int);
@@ -82,6 +83,7 @@ const char *cbnb_last_error_string(void) { return tl_error_msg; }
 const char *cbnb_version(void) { return "bnb_b200 sm_100a r1"; }
 long long cbnb_selftest_quant_lut(int qtype) { return selftest_quant_lut(qtype); }
 void cbnb_debug_gemv_probe(unsigned long long *cycles_ns) { gemv_probe(cycles_ns); }
+void cbnb_debug_gemv_trace(unsigned long long *out_2x320x8) { gemv_trace(out_2x320x8); }
 int cgemm_4bit_inference_nested_multi_fp16(int count, const int *m, int k, void *A, unsigned char **B, unsigned char **qabsmax, float **absmax2, float *code2, const float *offsets, float *datatype, void **outs, int blocksize, int blocksize2) {
   return gemv_4bit_nested_multi<half_t>(count, m, k, (half_t *)A, B, qabsmax, absmax2, code2, offsets, datatype, (half_t *const *)outs, blocksize, blocksize2, nullptr, 0); }
 int cgemm_4bit_inference_nested_multi_bf16(int count, const int *m, int k, void *A, unsigned char **B, unsigned char **qabsmax, float **absmax2, float *code2, const float *offsets, float *datatype, void **outs, int blocksize, int blocksize2) {

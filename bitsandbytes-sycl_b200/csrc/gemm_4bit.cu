@@ -269,13 +269,21 @@ struct WsBuf { float *p; size_t bytes; };
 static std::mutex g_ws_mu;
 static std::map<WsKey, WsBuf> g_ws;
 
-static float *workspace(int dev, size_t bytes, cudaStream_t st) {
+// *from_pool: stream capture in progress -> the buffer is a cudaMallocAsync allocation of the capturing stream (a node of
+// the graph); the caller frees it with cudaFreeAsync after the finalize kernel
+static float *workspace(int dev, size_t bytes, cudaStream_t st, bool *from_pool) {
+  *from_pool = false;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  if (cs != cudaStreamCaptureStatusNone) {
+    void *p = nullptr;
+    if (cudaMallocAsync(&p, bytes, st) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *from_pool = true;
+    return static_cast<float *>(p);
+  }
   std::lock_guard<std::mutex> lk(g_ws_mu);
   WsBuf &b = g_ws[WsKey{dev, st}];
   if (b.bytes >= bytes) return b.p;
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  cudaStreamIsCapturing(st, &cs);
-  if (cs != cudaStreamCaptureStatusNone) return nullptr;    // cannot grow inside a graph capture: caller falls back
   if (b.p) cudaFree(b.p);
   const size_t want = bytes < (size_t)(64u << 20) ? (size_t)(64u << 20) : bytes;
   if (cudaMalloc(&b.p, want) != cudaSuccess) { b.p = nullptr; b.bytes = 0; cudaGetLastError(); return nullptr; }
@@ -327,14 +335,18 @@ int gemm_4bit(int batch, int N, int K, const T *A, const unsigned char *B, const
   const int kb_per = (kblocks + splits - 1) / splits;
   a.kper = kb_per * TK;
   a.splits = (kblocks + kb_per - 1) / kb_per;
+  bool ws_from_pool = false;
   if (a.splits > 1) {
-    a.ws = workspace(dev, (size_t)a.splits * batch * N * sizeof(float), st);
+    a.ws = workspace(dev, (size_t)a.splits * batch * N * sizeof(float), st, &ws_from_pool);
     if (a.ws == nullptr) { a.splits = 1; a.kper = K; }
   }
 
   CUtensorMap tmX, tmW;
-  if (!make_tmap_2d(&tmX, A, 2, (uint64_t)batch, (uint64_t)K, (uint32_t)a.NB, TK, true, std::is_same<T, __nv_bfloat16>::value)) return 2;
-  if (!make_tmap_2d(&tmW, B, 1, (uint64_t)N, (uint64_t)(K / 2), TM, TK / 2, false, false, false)) return 2;
+  if (!make_tmap_2d(&tmX, A, 2, (uint64_t)batch, (uint64_t)K, (uint32_t)a.NB, TK, true, std::is_same<T, __nv_bfloat16>::value) ||
+      !make_tmap_2d(&tmW, B, 1, (uint64_t)N, (uint64_t)(K / 2), TM, TK / 2, false, false, false)) {
+    if (ws_from_pool) cudaFreeAsync(a.ws, st);
+    return 2;
+  }
   const size_t smem = (size_t)a.stages * stage_bytes + (size_t)a.wslots * kStageW + 1024 /*align*/ + 1024 /*barriers, code*/;
   static bool attr_set[2][64] = {{false}};      // per element type AND per device
   const int ti = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
@@ -350,6 +362,7 @@ int gemm_4bit(int batch, int N, int K, const T *A, const unsigned char *B, const
     if (blocks > num_sms[dev] * 8) blocks = num_sms[dev] * 8;
     k_gemm4_finalize<T><<<blocks, 256, 0, st>>>(a.ws, bias, out, a.splits, batch, N);
     check_launch("gemm_4bit (finalize)");
+    if (ws_from_pool) cudaFreeAsync(a.ws, st);
   }
   return 0;
 }

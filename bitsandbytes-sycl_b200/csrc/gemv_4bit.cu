@@ -18,9 +18,7 @@
 //     double-buffering (8 x 64-bit loads per lane in flight per chunk), deterministic smem reduction.
 // The MMA's n dimension carries the batch (1..8 activations rows) at no extra cost.
 #include <stdlib.h>
-#include <mutex>
 #include <type_traits>
-#include <unordered_map>
 
 #include "codebooks.cuh"
 #include "common.cuh"
@@ -60,7 +58,7 @@ template <> struct MmaT<__nv_bfloat16> {
 struct GemvArgs {
   int N, K, batch, blocksize;
   int bs_shift, bs2_shift;   // log2(blocksize), log2(blocksize2)
-  int flags;                 // bit 0: disable bulk L2 prefetch (experiments)
+  int flags;                 // bit 1: phase probe (debug)
   const void *x;             // [batch, K] T
   const unsigned char *B;    // [N, K/2]
   const float *absmax;       // fp32 [N*K/blocksize]            (plain)
@@ -100,23 +98,7 @@ struct GemvArgs {
   const unsigned int *epoch;
   unsigned int *cta_counter;    // per-GPU scratch, zero at rest
   int gidx, ngroups, do_signal, do_wait;
-  // next-weight hint (history prefetcher, see gemv_next_hint below): the packed weight and nested absmax the NEXT
-  // GEMV of this thread is expected to stream; every CTA pulls its share into L2 while this kernel is LSU-bound
-  const unsigned char *pf_ptr[2];
-  unsigned int pf_bytes[2];
 };
-
-// one warp pulls slice `part` of `nparts` of [p, p + bytes) into L2: bulk prefetches of <= 8 KB, no data returns to the SM
-__device__ __forceinline__ void l2_prefetch_slice(const unsigned char *p, unsigned int bytes, unsigned int part, unsigned int nparts, int lane) {
-  const unsigned int units = (bytes + 255u) >> 8;
-  const unsigned int b0 = (unsigned int)((unsigned long long)units * part / nparts) << 8;
-  unsigned int b1 = (unsigned int)((unsigned long long)units * (part + 1) / nparts) << 8;
-  if (b1 > (bytes & ~15u)) b1 = bytes & ~15u;
-  for (unsigned int off = b0 + (unsigned int)lane * 8192u; off < b1; off += 32u * 8192u) {
-    const unsigned int len = min(8192u, b1 - off);
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + off), "r"(len) : "memory");
-  }
-}
 
 // host-side mirror of bnb_gemv_sync_t (include/bnb_b200.h)
 struct GemvSync {
@@ -302,7 +284,7 @@ __device__ __forceinline__ uint4 lds_u128(uint32_t saddr) {
   return v;
 }
 
-template <typename T, bool NESTED, int EXP = 0>
+template <typename T, bool NESTED>
 __global__ void __launch_bounds__(kFastThreads, 1) k_gemv4_fast(const GemvArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
@@ -355,12 +337,6 @@ __global__ void __launch_bounds__(kFastThreads, 1) k_gemv4_fast(const GemvArgs a
     }
   };
   auto load = [&](FastBuf<NESTED> &b) {
-    if (EXP == 2) {  // experiment: no global weight traffic
-#pragma unroll
-      for (int s = 0; s < 4; s++) { b.w[s][0] = make_uint2(tid * 2654435761u + s, tid ^ 0x5bd1e995u); b.w[s][1] = make_uint2(tid * 40503u + s, tid * 97u); }
-      b.q[0] = b.q[1] = 0x80818283u; b.am2[0] = b.am2[1] = 1.0f; b.am4[0] = b.am4[1] = make_float4(1.f, 1.f, 1.f, 1.f);
-      return;
-    }
 #pragma unroll
     for (int s = 0; s < 4; s++) {
       b.w[s][0] = ld_stream_u2(wp0 + s * 4);
@@ -410,13 +386,6 @@ __global__ void __launch_bounds__(kFastThreads, 1) k_gemv4_fast(const GemvArgs a
   uint4 xa = make_uint4(0, 0, 0, 0), xb = make_uint4(0, 0, 0, 0);
 
   auto compute = [&](const FastBuf<NESTED> &b, int cc) {
-    if (EXP == 1) {  // experiment: memory stream only
-      uint32_t z = 0;
-#pragma unroll
-      for (int s = 0; s < 4; s++) z ^= b.w[s][0].x ^ b.w[s][0].y ^ b.w[s][1].x ^ b.w[s][1].y;
-      acc[0] += __uint_as_float(z & 0x3fffffffu) + (NESTED ? __uint_as_float(b.q[0] & 0x3fffffu) + b.am2[1] : b.am4[0].x);
-      return;
-    }
     float am[4][2];
     if (NESTED) {
 #pragma unroll
@@ -584,14 +553,17 @@ void peer_barrier(unsigned int *counter, const unsigned int *sig_local, unsigned
 }
 
 // debug probe (flags bit 1): SM cycles and nanoseconds spent by CTA 0 -> effective SM clock under this kernel's load
-__device__ unsigned long long g_gemv_probe[12];   // [0] cycles, [1] ns of the probed CTA; [2..6] phase timestamps (ns since entry)
+__device__ unsigned long long g_gemv_probe[12];
+// per-CTA trace (flags bit 2, debug): absolute globaltimer ns of {entry, loads issued, previous kernel complete, x ready,
+// all warps done, exit} + SM id, for the last two launches (slot = flags bit 3) -- tools/gemv_trace.py reads them
+__device__ unsigned long long g_gemv_trace[2][320][8];   // [0] cycles, [1] ns of the probed CTA; [2..6] phase timestamps (ns since entry)
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long v;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
   return v;
 }
 
-template <typename T, bool NESTED, int EXP = 0, int DEPTH = 2, int WARPS = 16, bool MULTI = false>
+template <typename T, bool NESTED, int DEPTH = 2, int WARPS = 16, bool MULTI = false>
 __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(const GemvArgs a, int x_blocks_padded, int tiles_total) {
   // shared memory: [0, 64 KB) byte LUT (entry stride 256 B, one word per lane) | code2 | x | partial sums.
   // The lookup address is  LUT base (uniform register) + PRMT(byte << 8 | lane * 4): no alignment requirement.
@@ -640,6 +612,13 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
   unsigned long long probe_c = 0, probe_t = 0;
   const bool probing = (a.flags & 2) && blockIdx.x == gridDim.x / 2 && tid == 0;
   if (probing) { probe_c = clock64(); probe_t = globaltimer_ns(); }
+  const bool tracing = (a.flags & 4) && tid == 0 && blockIdx.x < 320;
+  unsigned long long *tr = g_gemv_trace[(a.flags >> 3) & 1][blockIdx.x < 320 ? blockIdx.x : 0];
+  if (tracing) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    tr[0] = globaltimer_ns(); tr[6] = smid;
+  }
   const int kb = a.K >> 6;                 // blocks per row
   const int nch = (a.K + 511) >> 9;        // 512-element chunks per row (the last one may be half)
   const int row_bytes = a.K >> 1;
@@ -665,10 +644,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
     for (int h = 0; h < 2; h++) {
       const int row = min(lt * 16 + g + 8 * h, Nm - 1);
       const unsigned char *p = Bm + (size_t)row * row_bytes + c * 256 + (t + 4 * j) * 32;
-      if (EXP == 2) {   // experiment: compute only, no global weight traffic
-#pragma unroll
-        for (int i = 0; i < 8; i++) dst[h][i] = (uint32_t)(tid * 2654435761u) + i * 0x01010101u + c;
-      } else if (c * 8 + t + 4 * j < kb) ld_stream_u8(dst[h], p);
+      if (c * 8 + t + 4 * j < kb) ld_stream_u8(dst[h], p);
       else {
 #pragma unroll
         for (int i = 0; i < 8; i++) dst[h][i] = 0;
@@ -712,17 +688,12 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
     }
     advance(ltl, lc);
   }
-  if (warp == WARPS - 1) {
-#pragma unroll
-    for (int u = 0; u < 2; u++)
-      if (a.pf_bytes[u]) l2_prefetch_slice(a.pf_ptr[u], a.pf_bytes[u], blockIdx.x, gridDim.x, lane);
-  }
-
   // ---- prologue (overlaps the first weight loads): tables and partial-sum slots; everything here reads only
   // constants (code, code2), so it may run before the previous kernel of the stream has finished
   {
     constexpr int CT = WARPS * 32;
     if (probing) g_gemv_probe[7] = globaltimer_ns() - probe_t;      // first weight loads issued
+    if (tracing) { tr[1] = globaltimer_ns(); tr[7] = (unsigned long long)ntl; }
     // byte e -> {T(code[e >> 4]), T(code[e & 15])}, replicated for the 32 lanes (bank == lane): 8 threads write
     // one 128-byte entry with conflict-free 128-bit stores.  Thread (tid >> 3) + it * CT/8 handles entries whose low
     // nibble is fixed ((tid >> 3) & 15) and whose high nibble is a compile-time function of `it` plus bits of tid.
@@ -745,6 +716,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
     if (probing) g_gemv_probe[2] = globaltimer_ns() - probe_t;      // prologue (tables) done, about to wait
     asm volatile("griddepcontrol.wait;" ::: "memory");     // x (and out) belong to the previous kernel until here
     if (probing) g_gemv_probe[3] = globaltimer_ns() - probe_t;      // previous kernel complete
+    if (tracing) tr[2] = globaltimer_ns();
     if (a.sig_local != nullptr && a.do_wait) {
       // first kernel of a consumer group on an N-sharded stack: the gathered vectors of the previous group must
       // be complete on this GPU, i.e. every peer has published a sequence number >= ours (bounded spin: trap, never hang)
@@ -780,6 +752,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
   if (probing) g_gemv_probe[8] = globaltimer_ns() - probe_t;        // code2 arrived and stored
   __syncthreads();
   if (probing) g_gemv_probe[4] = globaltimer_ns() - probe_t;        // x in shared memory
+  if (tracing) tr[3] = globaltimer_ns();
 
   const uint32_t lane4 = (uint32_t)(lane * 4);
   const uint32_t act0 = (g == t), act1 = (g == t + 4);
@@ -799,7 +772,6 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
       for (int j = 0; j < 2; j++) {          // j = 0: blocks 0-3 (columns 0-3), j = 1: blocks 4-7 (columns 4-7)
 #pragma unroll
         for (int mg = 0; mg < 8; mg++) {     // one 32-bit word of each row = 8 elements = 2 MMAs
-          if (EXP == 1) { d[0] += __uint_as_float((w[s][j][0][mg] ^ w[s][j][1][mg]) & 0x3fffffffu); continue; }  // experiment: stream only
           if (j == 0) lds_x4_pred(b0, xc + mg * 16, act0);
           else lds_x4_pred(b1, xc + mg * 16, act1);
           const uint32_t s0 = w[s][j][0][mg], s1 = w[s][j][1][mg];
@@ -853,6 +825,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
   if (probing) g_gemv_probe[5] = globaltimer_ns() - probe_t;        // warp 0 finished its items
   __syncthreads();
   if (probing) g_gemv_probe[6] = globaltimer_ns() - probe_t;        // every warp finished
+  if (tracing) tr[4] = globaltimer_ns();
   for (int i = tid; i < ntl * 16; i += (WARPS * 32)) {
     const int tile_l = i >> 4, row = i & 15;
     const float *p = s_part + tile_l * WARPS * 16 + row;
@@ -892,6 +865,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
       }
     }
   }
+  if (tracing) tr[5] = globaltimer_ns();
   if (probing) {
     g_gemv_probe[0] = clock64() - probe_c;
     g_gemv_probe[1] = globaltimer_ns() - probe_t;
@@ -899,508 +873,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
 }
 
 #undef BNB_MSEL
-#include "gemv_v2.cuh"
-// ------------------------------------------------------------------------------------------------
-// TMA-staged block-column kernel (experiment, BNB_B200_GEMV_CFG=3x: measured equal to the register ring).
-//
-// Same arithmetic as k_gemv4_bc, different data movement.  Global loads issued by the compute warps share the
-// LSU / L1TEX pipe with the LUT lookups, and that pipe -- not HBM, not issue slots -- is what bounds this kernel
-// (measured: stream-only and compute-only each run at ~5.5 TB/s-equivalent, together at 3.4).  So the packed
-// weights never touch L1TEX: they are streamed by TMA (cp.async.bulk.tensor, two 16-row x 128-byte boxes per
-// item, 128-byte swizzle, out-of-bounds rows / columns zero-filled by the hardware) into a shared-memory ring
-// of `nslots` 4 KB slots, completion on one mbarrier per slot.  Item i of the CTA lives in slot i % nslots and
-// is consumed by warp i % WARPS: the warp waits for the slot, lifts its 4 KB into registers with eight
-// conflict-free LDS.128 and immediately re-arms the slot with the TMA loads of item i + nslots -- the consumer
-// of a slot is the producer of its next use (nslots is a multiple of WARPS, so a slot always belongs to the same
-// warp and its mbarrier phases are ordered by that warp's program order): there is no producer warp to fall
-// behind and no "empty" barrier.  The ring depth, not the register file, sets the bytes in flight towards HBM.
-// ------------------------------------------------------------------------------------------------
-constexpr int kBctSlot = 4096;                     // one item: 2 boxes of 16 rows x 128 B
-constexpr int kBctLut = 0;                         // [0, 64 KB): byte LUT, entry stride 256 B
-constexpr int kBctBars = 65536;                    // full[nslots] (8 B each), codeT
-constexpr int kBctCode2 = 65536 + 1024;
-constexpr int kBctRing = 65536 + 2048;             // 1024-byte aligned slots
-constexpr int kBctMaxSlots = 64;
-
-template <typename T, bool NESTED, int WARPS, int EXP = 0>
-__global__ void __launch_bounds__(WARPS * 32, 1)
-k_gemv4_bct(const GemvArgs a, const __grid_constant__ CUtensorMap tmapB, int x_blocks_padded, int tiles_total, int nslots) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // 128-byte-swizzled TMA destinations need 1024-byte alignment: align by hand (the launch adds 1 KB of slack)
-  const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
-  unsigned char *smem = smem_raw + (((raw_s + 1023u) & ~1023u) - raw_s);
-  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
-  uint32_t *s_codeT = reinterpret_cast<uint32_t *>(smem + kBctBars + kBctMaxSlots * 8);
-  float *s_code2 = reinterpret_cast<float *>(smem + kBctCode2);
-  unsigned char *s_x = smem + kBctRing + nslots * kBctSlot;
-  float *s_part = reinterpret_cast<float *>(s_x + (size_t)x_blocks_padded * kBcXPitch);   // [tile_local][warp][16]
-  const uint32_t full_s = smem_base + kBctBars;
-  const uint32_t ring_s = smem_base + kBctRing;
-  constexpr int CT = WARPS * 32;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned long long probe_c = 0, probe_t = 0;
-  if ((a.flags & 2) && blockIdx.x == 0 && tid == 0) { probe_c = clock64(); probe_t = globaltimer_ns(); }
-  const int kb = a.K >> 6;
-  const int nch = (a.K + 511) >> 9;
-  const int t_begin = (int)((long)blockIdx.x * tiles_total / gridDim.x);
-  const int t_end = (int)((long)(blockIdx.x + 1) * tiles_total / gridDim.x);
-  const int ntl = t_end - t_begin;
-  const int nitems = ntl * nch;
-
-  if (tid == 0) {
-    tc::prefetch_tmap(&tmapB);
-    for (int i = 0; i < nslots; i++) tc::mbar_init(full_s + i * 8, 1);
-    tc::fence_barrier_init();
-  }
-  __syncthreads();
-
-  auto issue = [&](int slot, int tl_, int c_) {   // one lane: arm the slot's barrier and start its two boxes
-    const uint32_t bar = full_s + slot * 8, dst = ring_s + slot * kBctSlot;
-    tc::mbar_arrive_expect_tx(bar, kBctSlot);
-    tc::tma_load_2d(dst, &tmapB, bar, c_ * 256, (t_begin + tl_) * 16);
-    tc::tma_load_2d(dst + 2048, &tmapB, bar, c_ * 256 + 128, (t_begin + tl_) * 16);
-  };
-  // first fill of the ring: item i (< nslots) is started by the warp that will consume it or one of its peers
-  if (lane == 0) {
-    for (int i = warp; i < nslots && i < nitems; i += WARPS) issue(i, i / nch, i % nch);
-  }
-
-  // ---- prologue (overlaps the first TMA loads): tables, activations, partial-sum slots
-  if (NESTED && tid < 256) s_code2[tid] = a.code2[tid];
-  if (tid < 16) s_codeT[tid] = MmaT<T>::pack(a.code[tid], 0.0f) & 0xFFFFu;
-  {
-    const uint4 *xg = reinterpret_cast<const uint4 *>(a.x);
-    const int pieces = x_blocks_padded * 8, valid = a.K >> 3;
-    for (int p0 = tid; p0 < pieces; p0 += 4 * CT) {
-      uint4 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int p = p0 + u * CT;
-        v[u] = p < valid ? __ldg(xg + p) : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int p = p0 + u * CT;
-        if (p < pieces) *reinterpret_cast<uint4 *>(s_x + (p >> 3) * kBcXPitch + (p & 7) * 16) = v[u];
-      }
-    }
-    for (int i = tid; i < ntl * WARPS * 16; i += CT) s_part[i] = 0.f;
-  }
-  __syncthreads();
-  {
-    const int j = tid & 7;
-    for (int e = tid >> 3; e < 256; e += CT / 8) {
-      const uint32_t v = s_codeT[e >> 4] | (s_codeT[e & 15] << 16);
-      *reinterpret_cast<uint4 *>(smem + kBctLut + e * 256 + j * 16) = make_uint4(v, v, v, v);
-    }
-  }
-  __syncthreads();
-
-  const int g = lane >> 2, t = lane & 3;
-  const uint32_t lane4 = (uint32_t)(lane * 4);
-  const uint32_t act0 = (g == t), act1 = (g == t + 4);
-  const uint32_t xlane = smem_base + (uint32_t)(kBctRing + nslots * kBctSlot) + g * kBcXPitch;
-  // this lane's two 16-byte pieces (q = 0, 1) of block t inside a swizzled 128-byte row: chunk (2t+q) ^ (row & 7)
-  const uint32_t wl0 = (uint32_t)(g * 128 + (((2 * t) ^ (g & 7)) << 4));
-  const uint32_t wl1 = (uint32_t)(g * 128 + (((2 * t + 1) ^ (g & 7)) << 4));
-  uint32_t b0[4] = {0, 0, 0, 0}, b1[4] = {0, 0, 0, 0};
-  float acc0 = 0.f, acc1 = 0.f;
-  const float offset = a.offset;
-  struct Abs { uint32_t q[2]; float am2[2]; float2 am[2]; };
-  auto load_abs = [&](Abs &d, int tile, int c) {
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int row = min(tile * 16 + g + 8 * h, a.N - 1);
-      const size_t idx = (size_t)row * kb + min(c * 8 + 2 * t, kb - 2);
-      if (NESTED) {
-        d.q[h] = __ldg(reinterpret_cast<const unsigned short *>(a.qabsmax + idx));
-        d.am2[h] = __ldg(a.absmax2 + (idx >> a.bs2_shift));
-      } else {
-        d.am[h] = __ldg(reinterpret_cast<const float2 *>(a.absmax + idx));
-      }
-    }
-  };
-  auto advance = [&](int &tl_, int &c_, int by) {
-    c_ += by;
-    while (c_ >= nch) { c_ -= nch; tl_++; }
-  };
-
-  int tl = 0, c = 0;                 // compute cursor: item `warp`
-  advance(tl, c, warp);
-  int itl = tl, ic = c;              // issue cursor: compute cursor + nslots items
-  advance(itl, ic, nslots);
-  int slot = warp % nslots;
-  uint32_t parity = (uint32_t)(warp / nslots) & 1u;
-  Abs cur, nxt;
-  if (tl < ntl) load_abs(cur, t_begin + tl, c);
-  for (int i = warp; i < nitems; i += WARPS) {
-    int ntl_ = tl, nc = c;
-    advance(ntl_, nc, WARPS);
-    if (ntl_ < ntl) load_abs(nxt, t_begin + ntl_, nc);
-    const uint32_t slot_s = ring_s + slot * kBctSlot;
-    if (EXP != 2 || i < nslots) tc::mbar_wait(full_s + slot * 8, parity);   // EXP 2: compute only, ring filled once
-    uint4 w[2][2][2];   // [block half j][row half h][q]
-#pragma unroll
-    for (int j = 0; j < 2; j++)
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        w[j][h][0] = lds_u128(slot_s + j * 2048 + h * 1024 + wl0);
-        w[j][h][1] = lds_u128(slot_s + j * 2048 + h * 1024 + wl1);
-      }
-    // the slot is free once every lane holds its bytes: wait for the loads (register dependency), then re-arm it
-    asm volatile("" ::"r"(w[0][0][0].x), "r"(w[0][1][0].x), "r"(w[1][0][0].x), "r"(w[1][1][0].x), "r"(w[0][0][1].x), "r"(w[0][1][1].x), "r"(w[1][0][1].x), "r"(w[1][1][1].x) : "memory");
-    __syncwarp();
-    if (EXP != 2 && lane == 0 && itl < ntl) {
-      tc::fence_proxy_async();        // generic-proxy reads of the slot before the async-proxy (TMA) overwrite
-      issue(slot, itl, ic);
-    }
-    advance(itl, ic, WARPS);
-    slot += WARPS;
-    while (slot >= nslots) { slot -= nslots; parity ^= 1u; }
-
-    const uint32_t xc = xlane + c * (8 * kBcXPitch);
-    float d[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < 2; j++) {
-#pragma unroll
-      for (int mg = 0; mg < 8; mg++) {
-        if (EXP == 1) {   // experiment: stream only
-          d[0] += __uint_as_float((w[j][0][mg >> 2].x ^ w[j][1][mg >> 2].y ^ w[j][0][mg >> 2].z ^ w[j][1][mg >> 2].w) & 0x3fffffffu);
-          continue;
-        }
-        if (j == 0) lds_x4_pred(b0, xc + mg * 16, act0);
-        else lds_x4_pred(b1, xc + mg * 16, act1);
-        const uint4 &v0 = w[j][0][mg >> 2], &v1 = w[j][1][mg >> 2];
-        const int wi = mg & 3;
-        const uint32_t s0 = wi == 0 ? v0.x : wi == 1 ? v0.y : wi == 2 ? v0.z : v0.w;
-        const uint32_t s1 = wi == 0 ? v1.x : wi == 1 ? v1.y : wi == 2 ? v1.z : v1.w;
-#pragma unroll
-        for (int mm = 0; mm < 2; mm++) {
-          // offset = byte * 256 + lane * 4 (one PRMT); the LUT base is a compile-time offset of the shared window
-          const uint32_t selA = 0x7604u | ((2 * mm) << 4), selB = 0x7604u | ((2 * mm + 1) << 4);
-          uint32_t af[4];
-          af[0] = *reinterpret_cast<const uint32_t *>(smem + kBctLut + __byte_perm(s0, lane4, selA));
-          af[1] = *reinterpret_cast<const uint32_t *>(smem + kBctLut + __byte_perm(s1, lane4, selA));
-          af[2] = *reinterpret_cast<const uint32_t *>(smem + kBctLut + __byte_perm(s0, lane4, selB));
-          af[3] = *reinterpret_cast<const uint32_t *>(smem + kBctLut + __byte_perm(s1, lane4, selB));
-          if (j == 0) MmaT<T>::mma(d, af, b0[2 * mm], b0[2 * mm + 1]);
-          else MmaT<T>::mma(d, af, b1[2 * mm], b1[2 * mm + 1]);
-        }
-      }
-    }
-    float am00, am01, am10, am11;
-    if (NESTED) {
-      am00 = __fadd_rn(__fmul_rn(s_code2[cur.q[0] & 0xFFu], cur.am2[0]), offset);
-      am01 = __fadd_rn(__fmul_rn(s_code2[cur.q[0] >> 8], cur.am2[0]), offset);
-      am10 = __fadd_rn(__fmul_rn(s_code2[cur.q[1] & 0xFFu], cur.am2[1]), offset);
-      am11 = __fadd_rn(__fmul_rn(s_code2[cur.q[1] >> 8], cur.am2[1]), offset);
-    } else {
-      am00 = cur.am[0].x; am01 = cur.am[0].y; am10 = cur.am[1].x; am11 = cur.am[1].y;
-    }
-    acc0 = __fmaf_rn(d[0], am00, acc0);
-    acc0 = __fmaf_rn(d[1], am01, acc0);
-    acc1 = __fmaf_rn(d[2], am10, acc1);
-    acc1 = __fmaf_rn(d[3], am11, acc1);
-    if (ntl_ != tl) {   // this warp is done with the tile: park its partial sums
-      acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
-      acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
-      acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
-      acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
-      if (t == 0) {
-        float *slot_p = s_part + (tl * WARPS + warp) * 16;
-        slot_p[g] = acc0;
-        slot_p[g + 8] = acc1;
-      }
-      acc0 = acc1 = 0.f;
-    }
-    tl = ntl_; c = nc; cur = nxt;
-  }
-  __syncthreads();
-  for (int i = tid; i < ntl * 16; i += CT) {
-    const int tile_l = i >> 4, row = i & 15;
-    const float *p = s_part + tile_l * WARPS * 16 + row;
-    float sum = 0.f;
-#pragma unroll
-    for (int wq = 0; wq < WARPS; wq++) sum += p[wq * 16];
-    const int r = (t_begin + tile_l) * 16 + row;
-    if (r < a.N) reinterpret_cast<T *>(a.out)[r] = from_float<T>(sum);
-  }
-  if ((a.flags & 2) && blockIdx.x == 0 && tid == 0) {
-    g_gemv_probe[0] = clock64() - probe_c;
-    g_gemv_probe[1] = globaltimer_ns() - probe_t;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// TMEM-staged block-column kernel: the packed weights never touch the LSU / L1TEX pipe.
-//
-// What bounds the block-column kernels above is the LSU data pipe (one 128-byte wavefront per clock per SM): the byte
-// LUT needs 128 wavefronts per 4 KB item, bringing the item into registers with LDG (or TMA + LDS) costs another
-// 32-50, the x fragments 32 and the scattered absmax loads ~20.  Here
-//   * the weights travel  HBM --TMA--> shared memory --tcgen05.cp--> TMEM --tcgen05.ld--> registers: three asynchronous
-//     engines, none of which uses an LSU wavefront, with a 256 KB TMEM ring (16 slots of 128 lanes x 32 columns) in
-//     front of the compute warps instead of a register ring;
-//   * a lane holds 16-BYTE pieces (half a quantisation block), so the lanes that feed x into one MMA sequence sit
-//     in ONE quarter-warp and their LDS.128 is a single wavefront (16 per item instead of 32);
-//   * the nested absmax bytes of the CTA's whole row range are copied to shared memory once, in the prologue.
-//
-// Stage = one 16-row tile x 1024 bytes of every row (8 half-chunks of 128 B = 2048 K elements) = 16 KB = four 4 KB
-// slots; slot q (TMEM lane quarter q, compute warp w with w % 4 == q) = half-chunks hc0+q and hc0+q+4.  The stage is
-// stored as eight planes p = (row half h, half-chunk jh, 64-byte piece jl) of [q][g][64 B] = 128 x 16 B: plane p is one
-// TMA box {64 B, 8 rows, 4 half-chunks} and one tcgen05.cp.128x128b (no swizzle, core matrix = 8 lanes x 16 B) into
-// TMEM columns [4p, 4p+4).  Lane (g,t) of slot q then owns, for rows g and g+8, the 16-byte pieces t of the four
-// 64-byte runs j = (jh, jl) of its slot: quantisation blocks 2j (t < 2) and 2j+1 (t >= 2) of the slot.
-//
-//   warp CW   (1 thread): TMA producer (weights are constants: runs ahead of griddepcontrol.wait)
-//   warp CW+1 (1 thread): TMEM owner + copier; tcgen05.commit frees the shared-memory stage and publishes the TMEM slot
-//   warps 0..CW-1       : compute; warp group w / 4 takes stages n = group (mod CW/4)
-// Arithmetic = k_gemv4_bc: one fp32 accumulator fragment runs through the 32 MMAs of an item; sequence j puts block 2j
-// in column 2j and block 2j+1 in column 2j+1, so afterwards lane (g,t) owns D[g | g+8][2t | 2t+1] = four distinct
-// (row, block) partial sums and applies the fp32 absmax once.  Same LUT, same exactness argument.
-// ------------------------------------------------------------------------------------------------
-constexpr int kTmStage = 16384;                    // 8 planes x 2 KB
-constexpr int kTmBars = 65536;                     // sfull[8] | sempty[8] | tfull[16] | tempty[16] | tmem slot
-constexpr int kTmCode2 = 65536 + 1024;
-constexpr int kTmRing = 65536 + 2048;
-constexpr int kTmSlots = 16;                       // TMEM ring: 512 columns / 32
-constexpr int kTmMaxStages = 8;
-constexpr int kTmXPitch = 80;                      // bytes per 32-element piece of x in shared memory (64 + 16: conflict-free)
-
-// K-major, no swizzle, one 16-byte core-matrix column: 8-row groups 128 B apart
-__device__ __forceinline__ uint64_t tm_desc_nosw(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(128u >> 4) << 16;                // leading byte offset (not used: a single core matrix along K)
-  d |= (uint64_t)(128u >> 4) << 32;                // stride byte offset between 8-row groups
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-__device__ __forceinline__ void tmem_cp_128x128b(uint32_t taddr, uint64_t sdesc) {
-  asm volatile("tcgen05.cp.cta_group::1.128x128b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap *m, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-
-template <typename T, bool NESTED, int CW>
-__global__ void __launch_bounds__((CW + 2) * 32, 1)
-k_gemv4_tm(const GemvArgs a, const __grid_constant__ CUtensorMap tmapB, int x_pieces_padded, int tiles_total, int nsmem, int abs_bytes) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
-  unsigned char *smem = smem_raw + (((raw_s + 1023u) & ~1023u) - raw_s);
-  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
-  const uint32_t sfull = smem_base + kTmBars, sempty = sfull + 64, tfull = sfull + 128, tempty = sfull + 256;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kTmBars + 384);
-  float *s_code2 = reinterpret_cast<float *>(smem + kTmCode2);
-  const uint32_t ring_s = smem_base + kTmRing;
-  unsigned char *s_x = smem + kTmRing + nsmem * kTmStage;
-  unsigned char *s_abs = s_x + (size_t)x_pieces_padded * kTmXPitch;                 // nested: qabsmax bytes of this CTA's rows
-  float *s_part = reinterpret_cast<float *>(s_abs + abs_bytes);                     // [tile_local][warp][16]
-  constexpr int G = CW / 4;
-  constexpr int CT = CW * 32;
-  asm volatile("griddepcontrol.launch_dependents;");
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int kb = a.K >> 6;                   // blocks per row
-  const int nhc = a.K >> 8;                  // 128-byte half-chunks per row
-  const int spt = (nhc + 7) >> 3;            // stages per tile
-  const int t_begin = (int)((long)blockIdx.x * tiles_total / gridDim.x);
-  const int t_end = (int)((long)(blockIdx.x + 1) * tiles_total / gridDim.x);
-  const int ntl = t_end - t_begin;
-  const int nstages = ntl * spt;
-
-  if (tid == CW * 32) {
-    tc::prefetch_tmap(&tmapB);
-    for (int i = 0; i < kTmMaxStages; i++) { tc::mbar_init(sfull + i * 8, 1); tc::mbar_init(sempty + i * 8, 1); }
-    for (int i = 0; i < kTmSlots; i++) { tc::mbar_init(tfull + i * 8, 1); tc::mbar_init(tempty + i * 8, 4); }
-    tc::fence_barrier_init();
-  }
-  if (warp == CW + 1) tc::tmem_alloc(tc::smem_u32(tmem_slot), 512);
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == CW) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      int tl = 0, si = 0;
-      for (int n = 0; n < nstages; n++) {
-        const int st = n % nsmem;
-        tc::mbar_wait(sempty + st * 8, ((uint32_t)(n / nsmem) & 1u) ^ 1u);
-        tc::mbar_arrive_expect_tx(sfull + st * 8, kTmStage);
-        const uint32_t dst = ring_s + st * kTmStage;
-#pragma unroll
-        for (int p = 0; p < 8; p++)   // plane p = (h, jh, jl)
-          tma_load_4d(dst + p * 2048, &tmapB, sfull + st * 8, 64 * (p & 1), 8 * (p >> 2), si * 8 + 4 * ((p >> 1) & 1), t_begin + tl);
-        if (++si == spt) { si = 0; tl++; }
-      }
-    }
-  } else if (warp == CW + 1) {
-    // ================= copier: shared memory -> TMEM =================
-    if (lane == 0) {
-      for (int n = 0; n < nstages; n++) {
-        const int st = n % nsmem, sl = n % kTmSlots;
-        tc::mbar_wait(sfull + st * 8, (uint32_t)(n / nsmem) & 1u);
-        tc::mbar_wait(tempty + sl * 8, ((uint32_t)(n / kTmSlots) & 1u) ^ 1u);
-        tc::fence_after_sync();
-        const uint32_t src = ring_s + st * kTmStage;
-#pragma unroll
-        for (int p = 0; p < 8; p++) tmem_cp_128x128b(tmem_base + sl * 32 + p * 4, tm_desc_nosw(src + p * 2048));
-        tc::umma_commit(sempty + st * 8);
-        tc::umma_commit(tfull + sl * 8);
-      }
-    }
-  } else {
-    // ================= compute warps =================
-    const int g = lane >> 2, t = lane & 3;
-    const int q = warp & 3, grp = warp >> 2;
-    // ---- prologue: tables, absmax bytes, partial-sum slots (constants only), then the activations (after the dependency wait)
-    {
-      for (int i = tid; i < 256; i += CT) if (NESTED) s_code2[i] = __ldg(a.code2 + i);
-      const int j = tid & 7;
-      for (int e = tid >> 3; e < 256; e += CT / 8) {
-        const uint32_t v = (MmaT<T>::pack(__ldg(a.code + (e >> 4)), 0.0f) & 0xFFFFu) | (MmaT<T>::pack(__ldg(a.code + (e & 15)), 0.0f) << 16);
-        *reinterpret_cast<uint4 *>(smem + e * 256 + j * 16) = make_uint4(v, v, v, v);
-      }
-      if (NESTED) {
-        const size_t first = (size_t)t_begin * 16 * kb, total = (size_t)a.N * kb;
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.qabsmax + first);
-        for (int i = tid; i < abs_bytes / 16; i += CT)
-          if (first + (size_t)i * 16 + 16 <= total) *reinterpret_cast<uint4 *>(s_abs + i * 16) = __ldg(src + i);
-      }
-      for (int i = tid; i < ntl * CW * 16; i += CT) s_part[i] = 0.f;
-      asm volatile("griddepcontrol.wait;" ::: "memory");     // x (and out) belong to the previous kernel until here
-      // x in shared memory: 32-element pieces at a pitch of 80 B (four consecutive pieces -> four distinct bank groups)
-      const uint4 *xg = reinterpret_cast<const uint4 *>(a.x);
-      const int units = x_pieces_padded * 4, valid = a.K >> 3;
-      for (int p0 = tid; p0 < units; p0 += 4 * CT) {
-        uint4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int p = p0 + u * CT;
-          v[u] = p < valid ? ld_x_u4(xg + p) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int p = p0 + u * CT;
-          if (p < units) *reinterpret_cast<uint4 *>(s_x + (p >> 2) * kTmXPitch + (p & 3) * 16) = v[u];
-        }
-      }
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
-
-    const uint32_t lane4 = (uint32_t)(lane * 4);
-    const int gsel = g - (t >> 1);                   // sequence j feeds x from the lanes with g == 2j + (t >> 1)
-    const uint32_t x_s = smem_base + (uint32_t)(kTmRing + nsmem * kTmStage) + (uint32_t)(t * kTmXPitch);
-    const float offset = a.offset;
-    const uint32_t taddr_q = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int bs2 = a.bs2_shift;
-    // this lane's four partial sums: rows g, g+8 x slot blocks 2t, 2t+1 = row blocks 4 * (hc0 + q + 4 * (t >> 1)) + 2 * (t & 1) (+1)
-    const int hsel = q + 4 * (t >> 1), bsel = 2 * (t & 1);
-
-    float acc0 = 0.f, acc1 = 0.f;
-    uint32_t b[4];
-    int tl = 0, si = grp;
-    while (si >= spt) { si -= spt; tl++; }
-    for (int n = grp; n < nstages; n += G) {
-      int ntl_ = tl, nsi = si + G;
-      while (nsi >= spt) { nsi -= spt; ntl_++; }
-      const int hc0 = si * 8;
-      // absmax of the four partial sums (clamped inside the row for zero-filled half-chunks: they multiply exact zeros)
-      const int rb = min((hc0 + hsel) * 4 + bsel, kb - 2);
-      float am00, am01, am10, am11;
-      {
-        const int row0 = (t_begin + tl) * 16 + g;
-        const size_t i0 = (size_t)row0 * kb + rb, i1 = i0 + (size_t)8 * kb;
-        if (NESTED) {
-          const uint32_t q0 = *reinterpret_cast<const unsigned short *>(s_abs + (size_t)(tl * 16 + g) * kb + rb);
-          const uint32_t q1 = *reinterpret_cast<const unsigned short *>(s_abs + (size_t)(tl * 16 + g + 8) * kb + rb);
-          const float m0 = __ldg(a.absmax2 + (i0 >> bs2)), m1 = __ldg(a.absmax2 + (i1 >> bs2));
-          am00 = __fadd_rn(__fmul_rn(s_code2[q0 & 0xFFu], m0), offset);
-          am01 = __fadd_rn(__fmul_rn(s_code2[q0 >> 8], m0), offset);
-          am10 = __fadd_rn(__fmul_rn(s_code2[q1 & 0xFFu], m1), offset);
-          am11 = __fadd_rn(__fmul_rn(s_code2[q1 >> 8], m1), offset);
-        } else {
-          const float2 f0 = __ldg(reinterpret_cast<const float2 *>(a.absmax + i0)), f1 = __ldg(reinterpret_cast<const float2 *>(a.absmax + i1));
-          am00 = f0.x; am01 = f0.y; am10 = f1.x; am11 = f1.y;
-        }
-      }
-      const int sl = n % kTmSlots;
-      tc::mbar_wait(tfull + sl * 8, (uint32_t)(n / kTmSlots) & 1u);
-      tc::fence_after_sync();
-      uint32_t v[32];
-      tc::tmem_ld_32x32b_x32(taddr_q + sl * 32, v);
-      tc::tmem_ld_wait();
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tempty + sl * 8);
-
-      float d[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int jh = 0; jh < 2; jh++) {
-        const int hc = hc0 + q + 4 * jh;
-        if (hc < nhc) {                            // warp-uniform: zero-filled half-chunks are skipped
-#pragma unroll
-          for (int jl = 0; jl < 2; jl++) {
-            const int j = 2 * jh + jl;
-            const uint32_t act = (gsel == 2 * j) ? 1u : 0u;
-            const uint32_t xj = x_s + (uint32_t)((hc * 8 + 4 * jl) * kTmXPitch);
-            b[0] = b[1] = b[2] = b[3] = 0u;
-#pragma unroll
-            for (int wd = 0; wd < 4; wd++) {
-              lds_x4_pred(b, xj + wd * 16, act);
-              const uint32_t s0 = v[4 * j + wd], s1 = v[16 + 4 * j + wd];
-#pragma unroll
-              for (int mm = 0; mm < 2; mm++) {
-                const uint32_t selA = 0x7604u | ((2 * mm) << 4), selB = 0x7604u | ((2 * mm + 1) << 4);
-                uint32_t af[4];
-                af[0] = *reinterpret_cast<const uint32_t *>(smem + __byte_perm(s0, lane4, selA));
-                af[1] = *reinterpret_cast<const uint32_t *>(smem + __byte_perm(s1, lane4, selA));
-                af[2] = *reinterpret_cast<const uint32_t *>(smem + __byte_perm(s0, lane4, selB));
-                af[3] = *reinterpret_cast<const uint32_t *>(smem + __byte_perm(s1, lane4, selB));
-                MmaT<T>::mma(d, af, b[2 * mm], b[2 * mm + 1]);
-              }
-            }
-          }
-        }
-      }
-      acc0 = __fmaf_rn(d[0], am00, acc0);
-      acc0 = __fmaf_rn(d[1], am01, acc0);
-      acc1 = __fmaf_rn(d[2], am10, acc1);
-      acc1 = __fmaf_rn(d[3], am11, acc1);
-      if (ntl_ != tl || n + G >= nstages) {   // this warp is done with the tile: park its partial sums
-        acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
-        acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
-        acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
-        acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
-        if (t == 0) {
-          float *slot = s_part + (tl * CW + warp) * 16;
-          slot[g] = acc0;
-          slot[g + 8] = acc1;
-        }
-        acc0 = acc1 = 0.f;
-      }
-      tl = ntl_; si = nsi;
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
-    for (int i = tid; i < ntl * 16; i += CT) {
-      const int tile_l = i >> 4, row = i & 15;
-      const float *p = s_part + tile_l * CW * 16 + row;
-      float sum = 0.f;
-#pragma unroll
-      for (int wq = 0; wq < CW; wq++) sum += p[wq * 16];
-      const int r = (t_begin + tile_l) * 16 + row;
-      if (r < a.N) reinterpret_cast<T *>(a.out)[r] = from_float<T>(sum);
-    }
-  }
-  tc::fence_before_sync();
-  __syncthreads();
-  if (warp == CW + 1) tc::tmem_dealloc(tmem_base, 512);
-}
-
+void gemv_trace(unsigned long long *out) { cudaMemcpyFromSymbol(out, g_gemv_trace, sizeof(unsigned long long) * 2 * 320 * 8); }
 // host: last probe of the block-column kernel -> {cycles, ns}
 void gemv_probe(unsigned long long *out2) {
   cudaMemcpyFromSymbol(out2, g_gemv_probe, sizeof(unsigned long long) * 12);
@@ -1451,176 +924,77 @@ static bool fast_path_ok(int K, int ldb, int blocksize, const void *A, const voi
 
 static int ilog2(int v) { int s = 0; while ((1 << s) < v) s++; return s; }
 
+// smem of the block-column kernel for `warps` warps per CTA on `grid` CTAs
+static size_t bc_smem_need(int K, int tiles, int warps, int grid) {
+  const int xblocks = ceil_div(K, 512) * 8;
+  return (size_t)65536 + kBcHead + (size_t)xblocks * kBcXPitch + (size_t)ceil_div(tiles, grid) * warps * 16 * sizeof(float);
+}
+static cudaLaunchConfig_t pdl_config(int grid, int threads, size_t smem, cudaLaunchAttribute *attr) {
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(grid); lc.blockDim = dim3(threads); lc.dynamicSmemBytes = smem; lc.stream = current_stream();
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr; lc.numAttrs = 1;
+  return lc;
+}
+// BNB_B200_GEMV_PROBE=1: the middle CTA records its phase timestamps (tools/kbench.py reads them); =2: every CTA of the last
+// two launches records absolute timestamps (tools/gemv_trace.py)
+static int probe_flag() {
+  static int v = -1;
+  static unsigned int seq = 0;
+  if (v < 0) { const char *pr = getenv("BNB_B200_GEMV_PROBE"); v = pr ? (pr[0] == '1' ? 2 : pr[0] == '2' ? 4 : 0) : 0; }
+  if (v == 4) return 4 | (int)((seq++ & 1u) << 3);
+  return v;
+}
+
 template <typename T, bool NESTED, bool VEC4>
 static void launch_mma_inst(const GemvArgs &a) {
-  static bool attr_set[64] = {false};
-  static int num_sms[64] = {0};
-  const size_t smem = VEC4 ? (size_t)kFastSmem
-                           : kGemvLutBytes + kGemvWarps * 128 * sizeof(float) + 256 * sizeof(float) + 16 * sizeof(uint32_t);
-  int dev = 0;
+  int dev = 0, sms = kNumSMs;
   cudaGetDevice(&dev);
-  dev = dev < 64 ? dev : 63;
-  auto kernel = VEC4 ? k_gemv4_fast<T, NESTED> : k_gemv4_mma<T, NESTED, false>;
-  static int exp_mode = -1, pf_off = 0;
-  if (exp_mode < 0) {
-    const char *e = getenv("BNB_B200_GEMV_EXP"); exp_mode = e ? atoi(e) : 0;
-    const char *f = getenv("BNB_B200_GEMV_PF"); pf_off = (f && f[0] == '0') ? 1 : 0;
-    const char *pr = getenv("BNB_B200_GEMV_PROBE"); if (pr && pr[0] == '1') pf_off |= 2;
-  }
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   GemvArgs a2 = a;
-  a2.flags = pf_off;
-  if (VEC4 && NESTED && exp_mode == 1) kernel = k_gemv4_fast<T, NESTED, 1>;
-  if (VEC4 && NESTED && exp_mode == 2) kernel = k_gemv4_fast<T, NESTED, 2>;
-  if (!attr_set[dev]) {
-    latch_error(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "gemv smem attr");
-    cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
-    attr_set[dev] = true;
-  }
-  static int impl_reg = -1, impl_bc = 1;
-  if (impl_reg < 0) {
-    const char *e = getenv("BNB_B200_GEMV_IMPL");
-    impl_reg = (e && e[0] == 'r') ? 1 : 0;
-    impl_bc = (e && (e[0] == 'r' || e[0] == 't')) ? 0 : 1;
-  }
-  static int pdl_off = -1;
-  if (pdl_off < 0) { const char *e = getenv("BNB_B200_GEMV_PDL"); pdl_off = (e && e[0] == '0') ? 1 : 0; }
-  static int cfg_t = -1;   // experiment knob: BNB_B200_GEMV_CFG = <impl><warps/4>: 3x = TMA ring, 1x/2x = register ring depth 1/2
-  if (cfg_t < 0) { const char *e = getenv("BNB_B200_GEMV_CFG"); cfg_t = e ? atoi(e) : 0; }
-  if (VEC4 && impl_bc && a.batch == 1 && cfg_t >= 30 && a.npeers == 0) {
-    const int warps = (cfg_t % 10) * 4;
+  a2.flags = probe_flag();
+  if (VEC4 && a.batch == 1) {
+    // block-column kernel, register ring.  8-warp CTAs, two per SM (<= 113 KB of shared memory and <= 128 registers
+    // each), so consecutive GEMVs of a stream overlap through programmatic dependent launch; 16-warp CTAs, one per
+    // SM, when x + partial sums do not fit twice (K > ~16K).
     const int tiles = ceil_div(a.N, 16);
-    const int grid = tiles < num_sms[dev] ? tiles : num_sms[dev];
-    const int xblocks = ceil_div(a.K, 512) * 8;
-    const int ntl_max = ceil_div(tiles, grid);
-    const size_t fixed = 1024 + kBctRing + (size_t)xblocks * kBcXPitch + (size_t)ntl_max * warps * 16 * sizeof(float);
-    int nslots = fixed < (size_t)kBcSmemMax ? (int)(((size_t)kBcSmemMax - fixed) / kBctSlot) : 0;
-    if (nslots > kBctMaxSlots) nslots = kBctMaxSlots;
-    const int items_max = ntl_max * ceil_div(a.K, 512);
-    (void)items_max;
-    { static int cap = -1; if (cap < 0) { const char *e = getenv("BNB_B200_GEMV_SLOTS"); cap = e ? atoi(e) : 0; } if (cap > 0 && nslots > cap) nslots = cap; }
-    // a slot must always be consumed (and re-armed) by the same warp -- that is what orders its mbarrier phases
-    // without an "empty" barrier -- so the ring holds a whole number of items per warp
-    nslots = (nslots / warps) * warps;
-    CUtensorMap tmap;
-    if (nslots >= warps && make_tmap_2d(&tmap, a.B, 1, (uint64_t)a.N, (uint64_t)(a.K / 2), 16, 128, false, false, true)) {
-      const size_t need = fixed + (size_t)nslots * kBctSlot;
-#define BCT_LAUNCH(WARPS_)                                                                                               \
-  do {                                                                                                                  \
-    auto kfn = exp_mode == 1 ? k_gemv4_bct<T, NESTED, WARPS_, 1> : exp_mode == 2 ? k_gemv4_bct<T, NESTED, WARPS_, 2> : k_gemv4_bct<T, NESTED, WARPS_, 0>;                                                                       \
-    latch_error(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kBcSmemMax), "gemv bct smem attr"); \
-    kfn<<<grid, WARPS_ * 32, need, current_stream()>>>(a2, tmap, xblocks, tiles, nslots);                         \
-  } while (0)
-      if (warps == 20) BCT_LAUNCH(20);
-      else if (warps == 24) BCT_LAUNCH(24);
-      else if (warps == 12) BCT_LAUNCH(12);
-      else BCT_LAUNCH(16);
-#undef BCT_LAUNCH
-      check_launch("gemv_4bit (TMA block-column)");
-      return;
+    int warps = 8;
+    int grid = tiles < sms * 2 ? tiles : sms * 2;
+    if (bc_smem_need(a.K, tiles, warps, grid) > (size_t)(113 * 1024)) {
+      warps = 16;
+      grid = tiles < sms ? tiles : sms;
     }
-  }
-  static int impl_tm = -1;
-  if (impl_tm < 0) { const char *e = getenv("BNB_B200_GEMV_IMPL"); impl_tm = (e && e[0] == 'm') ? 1 : 0; }
-  if (VEC4 && impl_tm && a.batch == 1 && a.npeers == 0 && (a.N % 16) == 0 && (reinterpret_cast<uintptr_t>(a.B) % 16 == 0) &&
-      (!NESTED || reinterpret_cast<uintptr_t>(a.qabsmax) % 16 == 0)) {
-    static int cw_env = -1;
-    if (cw_env < 0) { const char *e = getenv("BNB_B200_GEMV_TMW"); cw_env = e ? atoi(e) : 16; }
-    const int cw = cw_env == 12 ? 12 : 16;
-    const int tiles = a.N / 16;
-    const int grid = tiles < num_sms[dev] ? tiles : num_sms[dev];
-    const int nhc = a.K / 256, spt = ceil_div(nhc, 8), kb = a.K / 64;
-    const int xpieces = spt * 64;
-    const int ntl_max = ceil_div(tiles, grid);
-    const int abs_bytes = NESTED ? ((ntl_max * 16 * kb + 15) & ~15) : 0;
-    const size_t fixed = 1024 + kTmRing + (size_t)xpieces * kTmXPitch + abs_bytes + (size_t)ntl_max * cw * 16 * sizeof(float);
-    int nsmem = fixed < (size_t)kBcSmemMax ? (int)(((size_t)kBcSmemMax - fixed) / kTmStage) : 0;
-    { static int cap = -1; if (cap < 0) { const char *e = getenv("BNB_B200_GEMV_SLOTS"); cap = e ? atoi(e) : 6; } if (cap > 0 && nsmem > cap) nsmem = cap; }
-    if (nsmem > kTmMaxStages) nsmem = kTmMaxStages;
-    CUtensorMap tmap;
-    if (nsmem >= 2 && make_tmap_gemv_tm(&tmap, a.B, a.N, a.K)) {
-      const size_t need = fixed + (size_t)nsmem * kTmStage;
-      cudaLaunchConfig_t lc = {};
-      lc.gridDim = dim3(grid); lc.blockDim = dim3((cw + 2) * 32); lc.dynamicSmemBytes = need; lc.stream = current_stream();
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = 1;
-      lc.attrs = attr; lc.numAttrs = pdl_off ? 0 : 1;
-#define TM_LAUNCH(CW_)                                                                                                   \
-  do {                                                                                                                  \
-    auto kfn = k_gemv4_tm<T, NESTED, CW_>;                                                                              \
-    latch_error(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kBcSmemMax), "gemv tm smem attr"); \
-    latch_error(cudaLaunchKernelEx(&lc, kfn, a2, tmap, xpieces, tiles, nsmem, abs_bytes), "gemv_4bit (TMEM-staged) launch"); \
-  } while (0)
-      if (cw == 12) TM_LAUNCH(12);
-      else TM_LAUNCH(16);
-#undef TM_LAUNCH
-      check_launch("gemv_4bit (TMEM-staged)");
-      return;
-    }
-  }
-  static int impl_v2 = -1;
-  if (impl_v2 < 0) { const char *e = getenv("BNB_B200_GEMV_IMPL"); impl_v2 = (e && e[0] == '2') ? 1 : 0; }
-  if (VEC4 && impl_v2 && a.batch == 1 && !exp_mode && launch_v2<T, NESTED, false>(a2, ceil_div(a.N, 16), num_sms[dev])) return;
-  if (VEC4 && impl_bc && a.batch == 1) {
-    // block-column kernel, register ring.  Default: 8-warp CTAs, two per SM (<= 113 KB of shared memory and <= 128
-    // registers each), so consecutive GEMVs of a stream overlap through programmatic dependent launch; 16-warp
-    // CTAs, one per SM, when x + partial sums do not fit twice (K > ~16K).
-    static int cfg = -1;   // experiment knob: BNB_B200_GEMV_CFG = <depth><warps/4>, e.g. 22 = depth 2, 8 warps
-    if (cfg < 0) { const char *e = getenv("BNB_B200_GEMV_CFG"); cfg = e ? atoi(e) : 0; if (cfg >= 30) cfg = 0; }
-    const int tiles = ceil_div(a.N, 16);
-    const int xblocks = ceil_div(a.K, 512) * 8;
-    auto smem_need = [&](int warps, int grid) {
-      return (size_t)65536 + kBcHead + (size_t)xblocks * kBcXPitch + (size_t)ceil_div(tiles, grid) * warps * 16 * sizeof(float);
-    };
-    int warps = cfg ? (cfg % 10) * 4 : 8;
-    int per_sm = warps <= 8 ? 2 : 1;
-    static int grid_per_sm = -1;   // experiment knob: BNB_B200_GEMV_PERSM=1 -> one 8-warp CTA per SM per kernel, so the NEXT kernel's CTA is co-resident
-    if (grid_per_sm < 0) { const char *e = getenv("BNB_B200_GEMV_PERSM"); grid_per_sm = e ? atoi(e) : 0; }
-    if (grid_per_sm > 0 && grid_per_sm < per_sm) per_sm = grid_per_sm;
-    int grid = tiles < num_sms[dev] * per_sm ? tiles : num_sms[dev] * per_sm;
-    if (!cfg && smem_need(warps, grid) > (size_t)(113 * 1024)) {
-      warps = 16; per_sm = 1;
-      grid = tiles < num_sms[dev] ? tiles : num_sms[dev];
-    }
-    const size_t need = smem_need(warps, grid);
-    const int depth = cfg ? cfg / 10 : 2;
+    const size_t need = bc_smem_need(a.K, tiles, warps, grid);
     if (need <= (size_t)kBcSmemMax) {
-      cudaLaunchConfig_t lc = {};
-      lc.gridDim = dim3(grid); lc.blockDim = dim3(warps * 32); lc.dynamicSmemBytes = need; lc.stream = current_stream();
       cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = 1;
-      lc.attrs = attr; lc.numAttrs = pdl_off ? 0 : 1;
-#define BC_LAUNCH(EXP_, DEPTH_, WARPS_)                                                                                  \
-  do {                                                                                                                  \
-    auto kfn = k_gemv4_bc<T, NESTED, EXP_, DEPTH_, WARPS_>;                                                             \
-    latch_error(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kBcSmemMax), "gemv bc smem attr"); \
-    latch_error(cudaLaunchKernelEx(&lc, kfn, a2, xblocks, tiles), "gemv_4bit (block-column) launch");                  \
-  } while (0)
-      if (exp_mode == 1 && warps == 8) BC_LAUNCH(1, 2, 8);
-      else if (exp_mode == 2 && warps == 8) BC_LAUNCH(2, 2, 8);
-      else if (exp_mode == 1) BC_LAUNCH(1, 2, 16);
-      else if (exp_mode == 2) BC_LAUNCH(2, 2, 16);
-      else if (warps == 8 && depth == 1) BC_LAUNCH(0, 1, 8);
-      else if (warps == 8) BC_LAUNCH(0, 2, 8);
-      else if (warps == 12 && depth == 1) BC_LAUNCH(0, 1, 12);
-      else if (warps == 16 && depth == 1) BC_LAUNCH(0, 1, 16);
-      else if (warps == 20) BC_LAUNCH(0, 1, 20);
-      else if (warps == 24) BC_LAUNCH(0, 1, 24);
-      else BC_LAUNCH(0, 2, 16);
-#undef BC_LAUNCH
+      cudaLaunchConfig_t lc = pdl_config(grid, warps * 32, need, attr);
+      const int xblocks = ceil_div(a.K, 512) * 8;
+      if (warps == 8) {
+        auto kfn = k_gemv4_bc<T, NESTED, 2, 8>;
+        ensure_max_dynamic_smem(reinterpret_cast<const void *>(kfn), kBcSmemMax, "gemv bc smem attr");
+        latch_error(cudaLaunchKernelEx(&lc, kfn, a2, xblocks, tiles), "gemv_4bit (block-column) launch");
+      } else {
+        auto kfn = k_gemv4_bc<T, NESTED, 2, 16>;
+        ensure_max_dynamic_smem(reinterpret_cast<const void *>(kfn), kBcSmemMax, "gemv bc smem attr");
+        latch_error(cudaLaunchKernelEx(&lc, kfn, a2, xblocks, tiles), "gemv_4bit (block-column) launch");
+      }
       check_launch("gemv_4bit (block-column)");
       return;
     }
   }
   if (a.npeers > 0) { latch_error(cudaErrorInvalidValue, "gemv_4bit: peer outputs are only available in the block-column kernel"); return; }
+  // batch 2..8 (the batch rides in the MMA n dimension), blocksize != 64, K % 256 != 0: the per-block-accumulator kernels
   if (VEC4) {
-    const int tiles = ceil_div(a.N, 16);
-    const int ctas = ceil_div(tiles, kFastGroups);
-    const int grid = ctas < num_sms[dev] ? ctas : num_sms[dev];
-    kernel<<<grid, kFastThreads, smem, current_stream()>>>(a2);
+    auto kfn = k_gemv4_fast<T, NESTED>;
+    ensure_max_dynamic_smem(reinterpret_cast<const void *>(kfn), (int)kFastSmem, "gemv smem attr");
+    const int ctas = ceil_div(ceil_div(a.N, 16), kFastGroups);
+    kfn<<<ctas < sms ? ctas : sms, kFastThreads, kFastSmem, current_stream()>>>(a2);
   } else {
-    kernel<<<ceil_div(a.N, 16), kGemvThreads, smem, current_stream()>>>(a);
+    auto kfn = k_gemv4_mma<T, NESTED, false>;
+    const size_t smem = kGemvLutBytes + kGemvWarps * 128 * sizeof(float) + 256 * sizeof(float) + 16 * sizeof(uint32_t);
+    ensure_max_dynamic_smem(reinterpret_cast<const void *>(kfn), (int)smem, "gemv smem attr");
+    kfn<<<ceil_div(a.N, 16), kGemvThreads, smem, current_stream()>>>(a);
   }
   check_launch("gemv_4bit (mma)");
 }
@@ -1653,62 +1027,6 @@ void gemv_4bit(int m, int n, int k, const T *A, const unsigned char *B, const fl
   }
   k_gemv4_simple<T><<<ceil_div(m, 4), 128, 0, current_stream()>>>(m, k, A, B, absmax, datatype, out, ldb, blocksize);
   check_launch("gemv_4bit (generic)");
-}
-
-// ------------------------------------------------------------------------------------------------
-// Next-weight prefetcher.  Token-by-token decoding calls the same weights in the same order over and over, and a
-// batch-1 GEMV is bound by the shared-memory lookup pipe, not by HBM: while GEMV i runs, HBM has
-// room to bring the weight of GEMV i+1 into the 126 MB L2.  The library remembers, per packed-weight pointer, which
-// weight was streamed next the last time (a one-entry Markov table) and passes it to the kernel as a HINT; every
-// CTA issues bulk L2 prefetches for its share.  A hint is advisory: a wrong one costs bandwidth, never
-// correctness; a hint whose range is not inside a live device allocation (cuMemGetAddressRange) is dropped.
-// BNB_B200_GEMV_NEXTPF=0 switches the prefetcher off; cbnb_gemv_set_next_weight() overrides the history.
-// ------------------------------------------------------------------------------------------------
-struct NextHint { const void *B; size_t bytes; const void *q; size_t qbytes; };
-static std::mutex g_pf_mu;
-static std::unordered_map<const void *, NextHint> g_pf_next;
-static thread_local const void *tl_prev_B = nullptr;
-static thread_local NextHint tl_forced_hint = {nullptr, 0, nullptr, 0};
-void gemv_set_next_weight(const void *B, size_t bytes, const void *q, size_t qbytes) { tl_forced_hint = NextHint{B, bytes, q, qbytes}; }
-
-static bool device_range_ok(const void *p, size_t bytes) {
-  typedef CUresult (*fn_t)(CUdeviceptr *, size_t *, CUdeviceptr);
-  static fn_t fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void *q = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &q, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<fn_t>(q);
-  }
-  if (!fn || !p || !bytes) return false;
-  CUdeviceptr base = 0;
-  size_t size = 0;
-  if (fn(&base, &size, (CUdeviceptr)(uintptr_t)p) != CUDA_SUCCESS) return false;
-  return (uintptr_t)p + bytes <= (uintptr_t)base + size;
-}
-
-static void next_hint(GemvArgs &a, const void *B, size_t bytes, const void *q, size_t qbytes) {
-  static int off = -1;
-  if (off < 0) { const char *e = getenv("BNB_B200_GEMV_NEXTPF"); off = (e && e[0] == '0') ? 1 : 0; }
-  if (off) return;
-  NextHint h{nullptr, 0, nullptr, 0};
-  if (tl_forced_hint.B) { h = tl_forced_hint; tl_forced_hint = NextHint{nullptr, 0, nullptr, 0}; }
-  {
-    std::lock_guard<std::mutex> lk(g_pf_mu);
-    if (!h.B) { auto it = g_pf_next.find(B); if (it != g_pf_next.end()) h = it->second; }
-    if (tl_prev_B && tl_prev_B != B) g_pf_next[tl_prev_B] = NextHint{B, bytes, q, qbytes};
-    if (g_pf_next.size() > 65536) g_pf_next.clear();
-  }
-  tl_prev_B = B;
-  // a next weight that would not stay in the 126 MB L2 next to the current one is not worth pulling early
-  if (h.B && h.B != B && h.bytes <= (size_t)(40u << 20) && bytes <= (size_t)(64u << 20) && (reinterpret_cast<uintptr_t>(h.B) % 16) == 0 && device_range_ok(h.B, h.bytes)) {
-    a.pf_ptr[0] = static_cast<const unsigned char *>(h.B); a.pf_bytes[0] = (unsigned int)h.bytes;
-    if (h.q && h.qbytes < (1ull << 31) && (reinterpret_cast<uintptr_t>(h.q) % 16) == 0 && device_range_ok(h.q, h.qbytes)) {
-      a.pf_ptr[1] = static_cast<const unsigned char *>(h.q); a.pf_bytes[1] = (unsigned int)h.qbytes;
-    }
-  }
 }
 
 // host copies of code[16] / code2[256] for the NEXT nested GEMV of this thread (consumed by that call)
@@ -1756,7 +1074,6 @@ void gemv_4bit_nested(int m, int n, int k, const T *A, const unsigned char *B, c
       for (int i = 0; i < npeers; i++) a.sig_peer[i] = sync->sig_peer[i];
     }
   }
-  if (n == 1) next_hint(a, B, (size_t)m * (size_t)(k / 2), qabsmax, (size_t)m * (size_t)(k / blocksize));
   launch_mma<T, true>(a, blocksize2);
 }
 
@@ -1795,31 +1112,20 @@ int gemv_4bit_nested_multi(int count, const int *ms, int k, const T *A, const un
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int xblocks = ceil_div(k, 512) * 8;
-  auto smem_need = [&](int warps, int grid) {
-    return (size_t)65536 + kBcHead + (size_t)xblocks * kBcXPitch + (size_t)ceil_div(tiles, grid) * warps * 16 * sizeof(float);
-  };
-  {
-    static int impl_v2 = -1;
-    if (impl_v2 < 0) { const char *e = getenv("BNB_B200_GEMV_IMPL"); impl_v2 = (e && e[0] == '2') ? 1 : 0; }
-    if (impl_v2 && launch_v2<T, true, true>(a, tiles, sms)) return 0;
-  }
   int warps = 8, grid = tiles < sms * 2 ? tiles : sms * 2;
-  if (smem_need(warps, grid) > (size_t)(113 * 1024)) { warps = 16; grid = tiles < sms ? tiles : sms; }
-  const size_t need = smem_need(warps, grid);
+  if (bc_smem_need(k, tiles, warps, grid) > (size_t)(113 * 1024)) { warps = 16; grid = tiles < sms ? tiles : sms; }
+  const size_t need = bc_smem_need(k, tiles, warps, grid);
   if (need > (size_t)kBcSmemMax) return 1;
-  cudaLaunchConfig_t lc = {};
-  lc.gridDim = dim3(grid); lc.blockDim = dim3(warps * 32); lc.dynamicSmemBytes = need; lc.stream = current_stream();
+  a.flags = probe_flag();
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  lc.attrs = attr; lc.numAttrs = 1;
+  cudaLaunchConfig_t lc = pdl_config(grid, warps * 32, need, attr);
   if (warps == 8) {
-    auto kfn = k_gemv4_bc<T, true, 0, 2, 8, true>;
-    latch_error(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kBcSmemMax), "gemv multi smem attr");
+    auto kfn = k_gemv4_bc<T, true, 2, 8, true>;
+    ensure_max_dynamic_smem(reinterpret_cast<const void *>(kfn), kBcSmemMax, "gemv multi smem attr");
     latch_error(cudaLaunchKernelEx(&lc, kfn, a, xblocks, tiles), "gemv_4bit (multi) launch");
   } else {
-    auto kfn = k_gemv4_bc<T, true, 0, 2, 16, true>;
-    latch_error(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kBcSmemMax), "gemv multi smem attr");
+    auto kfn = k_gemv4_bc<T, true, 2, 16, true>;
+    ensure_max_dynamic_smem(reinterpret_cast<const void *>(kfn), kBcSmemMax, "gemv multi smem attr");
     latch_error(cudaLaunchKernelEx(&lc, kfn, a, xblocks, tiles), "gemv_4bit (multi) launch");
   }
   check_launch("gemv_4bit (multi)");

@@ -64,22 +64,6 @@ bool make_tmap_2d(CUtensorMap *map, const void *base, int elem_bytes, uint64_t r
   return true;
 }
 
-// packed 4-bit weight [N, K/2] seen as {128 B inside a half-chunk, 16 rows of a tile, K/256 half-chunks, N/16 tiles};
-// box {64 B, 8 rows, 4 half-chunks, 1 tile} lands in shared memory as [half-chunk][row][64 B], no swizzle (gemv_4bit.cu)
-bool make_tmap_gemv_tm(CUtensorMap *map, const void *base, int N, int K) {
-  auto fn = get_encode_fn();
-  if (!fn) { latch_error(cudaErrorNotSupported, "cuTensorMapEncodeTiled unavailable"); return false; }
-  const uint64_t row_bytes = (uint64_t)K / 2;
-  cuuint64_t dims[4] = {128, 16, (uint64_t)K / 256, (uint64_t)N / 16};
-  cuuint64_t strides[3] = {row_bytes, 128, row_bytes * 16};
-  cuuint32_t box[4] = {64, 8, 4, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { latch_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (gemv) failed"); return false; }
-  return true;
-}
-
 // ------------------------------------------------------------------------------------------------
 // tcgen05 kernel
 // ------------------------------------------------------------------------------------------------
@@ -475,15 +459,23 @@ struct LtKey { int dev; cudaStream_t st; bool operator<(const LtKey &o) const { 
 struct LtBuf { signed char *p; size_t bytes; };
 static std::mutex g_lt_mu;
 static std::map<LtKey, LtBuf> g_lt;
-static signed char *lt_scratch(size_t bytes, cudaStream_t st) {
+// *from_pool: the buffer came from cudaMallocAsync (stream capture in progress: the allocation becomes a node of the graph)
+// and must be handed back with cudaFreeAsync after the last kernel that uses it
+static signed char *lt_scratch(size_t bytes, cudaStream_t st, bool *from_pool) {
+  *from_pool = false;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  if (cs != cudaStreamCaptureStatusNone) {
+    void *p = nullptr;
+    if (cudaMallocAsync(&p, bytes, st) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *from_pool = true;
+    return static_cast<signed char *>(p);
+  }
   int dev = 0;
   cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lk(g_lt_mu);
   LtBuf &b = g_lt[LtKey{dev, st}];
   if (b.bytes >= bytes) return b.p;
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  cudaStreamIsCapturing(st, &cs);
-  if (cs != cudaStreamCaptureStatusNone) return nullptr;    // cannot grow inside a graph capture
   if (b.p) cudaFree(b.p);
   if (cudaMalloc(&b.p, bytes) != cudaSuccess) { b.p = nullptr; b.bytes = 0; cudaGetLastError(); return nullptr; }
   b.bytes = bytes;
@@ -502,20 +494,25 @@ int igemmlt(int fmtB, int dtype_out, bool scale_rows, int m, int n, int k, const
   if (scale_rows && row_scale == nullptr) return 2;
   cudaStream_t st = current_stream();
   const size_t szA = ((size_t)m * k + 255) & ~(size_t)255, szB = ((size_t)n * k + 255) & ~(size_t)255;
-  signed char *scratch = lt_scratch(szA + szB, st);
+  bool from_pool = false;
+  signed char *scratch = lt_scratch(szA + szB, st, &from_pool);
   if (scratch == nullptr) { latch_error(cudaErrorMemoryAllocation, "igemmlt scratch"); return 2; }
   signed char *Arm = scratch, *Brm = scratch + szA;
   untransform_s8(COL32, A, Arm, m, k);
   untransform_s8(fmtB, B, Brm, n, k);
   IgemmArgs a{};
   a.M = m; a.N = n; a.K = k;
+  int rc;
   if (dtype_out == 32) {
     a.C = reinterpret_cast<int *>(C);
-    return igemm_rowmajor<EPI_INT32_COL32>(Arm, Brm, a);
+    rc = igemm_rowmajor<EPI_INT32_COL32>(Arm, Brm, a);
+  } else {
+    a.C8 = reinterpret_cast<signed char *>(C);
+    a.row_scale = scale_rows ? row_scale : nullptr;
+    rc = igemm_rowmajor<EPI_S8_COL32>(Arm, Brm, a);
   }
-  a.C8 = reinterpret_cast<signed char *>(C);
-  a.row_scale = scale_rows ? row_scale : nullptr;
-  return igemm_rowmajor<EPI_S8_COL32>(Arm, Brm, a);
+  if (from_pool) cudaFreeAsync(scratch, st);
+  return rc;
 }
 
 }  // namespace bnb

@@ -1,7 +1,7 @@
 // tcgen05.cuh -- thin inline-PTX layer for the Blackwell (sm_100a) tensor path used by the GEMM kernels:
 // mbarrier, TMA (cp.async.bulk.tensor), TMEM allocation, tcgen05.mma / commit / ld, UMMA descriptors.
 // Descriptor bit layouts follow the PTX ISA "tcgen05 matrix / instruction descriptor" tables
-// (cross-checked against cute/arch/mma_sm100_desc.hpp in the vendored CUTLASS headers).
+// (cross-checked against cute/arch/mma_sm100_desc.hpp of the CUTLASS headers that ship inside the image's flashinfer package; nothing of CUTLASS is vendored or included here).
 #pragma once
 #include <cuda.h>
 #include <stdint.h>
@@ -128,6 +128,5 @@ bool make_tmap_2d(CUtensorMap *map, const void *base, int elem_bytes, uint64_t r
                   uint32_t box_cols, bool is_bf16_or_f16, bool is_bf16, bool swizzle128 = true);
 
 // host: tensor map of the TMEM-staged GEMV (gemv_4bit.cu k_gemv4_tm; defined in igemm.cu)
-bool make_tmap_gemv_tm(CUtensorMap *map, const void *base, int N, int K);
 
 }  // namespace bnb

@@ -135,6 +135,7 @@ BNB_B200_API long long cbnb_selftest_quant_lut(int qtype);
  * memory, (5) finished warp 0's items, (6) finished every warp's items; (7) first weight loads issued, (8) code2 stored, (9) LUT stored; out[10..11] unused.  Recorded only when the
  * environment has BNB_B200_GEMV_PROBE=1. */
 BNB_B200_API void cbnb_debug_gemv_probe(unsigned long long *cycles_ns);
+BNB_B200_API void cbnb_debug_gemv_trace(unsigned long long *out_2x320x8);
 
 /* GEMV with the NESTED (double-quantised) absmax consumed directly: qabsmax uint8 [N*K/blocksize],
  * absmax2 fp32 [ceil(nblocks/blocksize2)], code2 fp32[256], offset scalar. De-nesting is
