@@ -622,8 +622,14 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(con
   const int kb = a.K >> 6;                 // blocks per row
   const int nch = (a.K + 511) >> 9;        // 512-element chunks per row (the last one may be half)
   const int row_bytes = a.K >> 1;
-  const int t_begin = (int)(blockIdx.x * (unsigned)tiles_total / gridDim.x);          // < 2^32: grid <= 2 * 148, tiles < 2^22
-  const int t_end = (int)((blockIdx.x + 1) * (unsigned)tiles_total / gridDim.x);
+  // Tile ranges, HEAVY FIRST: CTAs are dispatched in blockIdx order as slots free up, so in a chain of launches the
+  // highest block indices enter last (they inherit the slots of the previous kernel's stragglers).  Giving the extra
+  // tile to the lowest indices keeps the late entrants light (per-CTA trace: with the interleaved split the last CTA
+  // of 11008x4096 entered 3.3 us late AND owned 3 tiles instead of 2 -- 3 us of an 8.5 us period was that tail).
+  const int tq = tiles_total / (int)gridDim.x, trem = tiles_total % (int)gridDim.x;
+  const int bx = (int)blockIdx.x;
+  const int t_begin = bx < trem ? bx * (tq + 1) : trem * (tq + 1) + (bx - trem) * tq;
+  const int t_end = t_begin + tq + (bx < trem ? 1 : 0);
   const int ntl = t_end - t_begin;
 
   uint32_t w[DEPTH][2][2][8];   // [ring slot][block t / t+4][row half][32 bytes = one sector per lane]

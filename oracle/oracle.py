@@ -319,6 +319,54 @@ def llm_int8_forward(A_f16: np.ndarray, CB: np.ndarray, SCB: np.ndarray, bias_f1
     return y, CA, row_stats, idx
 
 
+def llm_int8_backward(grad_f16: np.ndarray, A_f16: np.ndarray, threshold: float, CB: Optional[np.ndarray] = None,
+                      SCB: Optional[np.ndarray] = None, W_f16: Optional[np.ndarray] = None, need_grad_B: bool = False):
+    """CPU restatement of MatMul8bitLt.backward (reference python_src_quants/autograd/_functions.py:436-483), composed
+    from the per-kernel restatements.  grad [m, n] fp16, A [m, k] fp16 (the forward's input).
+      :454      Cgrad, Cgradt, SCgrad, SCgradt = double_quant(grad)                      (no threshold)
+      :455-461  grad_B = mm_dequant(igemmlt(Cgradt^T, CAt^T), SCgradt, SCAt) (+ grad^T @ subA on the outlier columns):
+                CAt / SCAt are the forward's column-quantised activations with the outlier columns zeroed (:382-383)
+      :462-468  has_fp16_weights (CBt from double_quant(W)):  grad_A = mm_dequant(igemmlt(Cgrad, CBt^T), SCgrad, SCBt)
+      :470-472  frozen int8 weight (CB, SCB):  grad_A = grad @ (CB.to(fp16) * (SCB / 127))     (16-bit GEMM)
+    Returns (grad_A fp16 [m, k], grad_B fp16 [n, k] | None).  The int8 parts are exact; the two 16-bit GEMMs are
+    restated with fp32 accumulation and one rounding (the BLAS's summation order is not specified)."""
+    G = np.ascontiguousarray(grad_f16, np.float16)
+    A = np.ascontiguousarray(A_f16, np.float16)
+    m, n = G.shape
+    k = A.shape[1]
+    g_rs, g_cs, _ = get_col_row_stats(G, 0.0)
+    Cgrad, Cgradt, _, _, _ = double_rowcol_quant(G, g_rs, g_cs)
+    grad_B = None
+    if need_grad_B:
+        a_rs, a_cs, nnz = get_col_row_stats(A, threshold)
+        if threshold > 0.0:
+            ptr = np.cumsum(nnz, dtype=np.int64).astype(np.int32)
+            _, CAt, _, colidx, _ = double_rowcol_quant(A, a_rs, a_cs, ptr, threshold)
+            idx = np.unique(colidx).astype(np.int64) if colidx is not None and colidx.size else np.zeros(0, np.int64)
+        else:
+            _, CAt, _, _, _ = double_rowcol_quant(A, a_rs, a_cs)
+            idx = np.zeros(0, np.int64)
+        CAt = CAt.copy()
+        if idx.size:
+            CAt[:, idx] = 0
+        acc = igemm_rowmajor(np.ascontiguousarray(Cgradt.T), np.ascontiguousarray(CAt.T))          # [n, k]
+        grad_B = mm_dequant(acc, g_cs, a_cs, n, k, None, col32=False)
+        if idx.size:
+            side = (G.astype(np.float32).T @ A[:, idx].astype(np.float32)).astype(np.float16)
+            grad_B[:, idx] = (grad_B[:, idx].astype(np.float32) + side.astype(np.float32)).astype(np.float16)
+    if W_f16 is not None:            # has_fp16_weights: CBt = column-quantised W
+        W = np.ascontiguousarray(W_f16, np.float16)
+        w_rs, w_cs, _ = get_col_row_stats(W, 0.0)
+        _, CBt, _, _, _ = double_rowcol_quant(W, w_rs, w_cs)
+        acc = igemm_rowmajor(Cgrad, np.ascontiguousarray(CBt.T))                                   # [m, k]
+        grad_A = mm_dequant(acc, g_rs, w_cs, m, k, None, col32=False)
+    else:
+        # CB.to(fp16).mul_(SCB.unsqueeze(1).mul(1/127)): the product is formed in fp32 and rounded to fp16 once
+        Wd = (CB.astype(np.float32) * (np.asarray(SCB, np.float32)[:, None] * np.float32(1.0 / 127.0))).astype(np.float16)
+        grad_A = (G.astype(np.float32) @ Wd.astype(np.float32)).astype(np.float16)
+    return grad_A, grad_B
+
+
 def extract_outliers(A_fmt: np.ndarray, idx: np.ndarray, rows: int, cols: int, fmt: str) -> np.ndarray:
     idx = np.ascontiguousarray(idx, np.int32)
     out = np.zeros((rows, idx.size), np.int8)

@@ -288,3 +288,49 @@ def test_matmul_4bit_multi_matches_linear4bit_modules(F):
                                           biases=[lin.bias.to(torch.bfloat16) for lin in lins])
     for a, b in zip(ref + ref8, got + got8):
         assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+def test_peer_store_epilogue_and_barrier_emulated_on_one_gpu(F, dtype):
+    """The multi-GPU data plane on ONE device: `peer_outs` are ordinary device buffers standing in for the peer-mapped
+    copies of the output vector (the kernel cannot tell), so every store of the fused all-gather epilogue
+    (cgemm_4bit_inference_nested_push_* and its multi-matrix form) is checked bit for bit; cbnb_peer_barrier runs with
+    its "peer" slots pointing at its own signal words (each rank publishes to itself), which exercises the sequence
+    counting and the bounded wait without a second process (B200_PROFILING.md: never spin on another launch)."""
+    import ctypes as ct
+    N, K = 1024, 4096
+    W, x, q, st = make_case(F, N, K, dtype, seed=91)
+    xc = x.cuda()
+    ref = F.gemv_4bit(xc, q.t(), state=st)
+    npeers = 3
+    peers = [torch.zeros(1, N, dtype=DT[dtype], device="cuda") for _ in range(npeers)]
+    out = torch.zeros(1, N, dtype=DT[dtype], device="cuda")
+    F.gemv_4bit(xc, q.t(), out=out, state=st, peer_outs=[p.data_ptr() for p in peers])
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int16), ref.view(torch.int16))
+    for p in peers:
+        assert torch.equal(p.view(torch.int16), ref.view(torch.int16))
+    # several matrices that share x, one launch, peer copies of every output slice
+    W2, _, q2, st2 = make_case(F, 512, K, dtype, seed=92)
+    ref2 = F.gemv_4bit(xc, q2.t(), state=st2)
+    outs = [torch.zeros(1, N, dtype=DT[dtype], device="cuda"), torch.zeros(1, 512, dtype=DT[dtype], device="cuda")]
+    pm = [[torch.zeros(1, n_, dtype=DT[dtype], device="cuda") for _ in range(2)] for n_ in (N, 512)]
+    F.gemv_4bit_multi(xc, [q.t(), q2.t()], [st, st2], outs=outs, peer_outs=[[p.data_ptr() for p in row] for row in pm])
+    torch.cuda.synchronize()
+    for got, want, row in ((outs[0], ref, pm[0]), (outs[1], ref2, pm[1])):
+        assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+        for p in row:
+            assert torch.equal(p.view(torch.int16), want.view(torch.int16))
+    # the PDL-chained barrier: two "peers" whose slots are this rank's own slots
+    sig = torch.zeros(8, dtype=torch.int32, device="cuda")
+    counter = torch.zeros(1, dtype=torch.int32, device="cuda")
+    arr = (ct.c_void_p * 2)(sig.data_ptr(), sig.data_ptr() + 4)
+    F.lib.cbnb_set_stream(ct.c_void_p(torch.cuda.current_stream().cuda_stream))
+    for it in range(1, 4):
+        F.gemv_4bit(xc, q.t(), out=out, state=st)                     # the barrier is a link of the PDL chain after a GEMV
+        F.lib.cbnb_peer_barrier(ct.c_void_p(counter.data_ptr()), ct.c_void_p(sig.data_ptr()), arr, ct.c_int32(2))
+        y = F.gemv_4bit(xc, q.t(), state=st)                          # ... and in front of the next one
+        torch.cuda.synchronize()
+        assert int(counter.item()) == it and sig[:2].tolist() == [it, it]
+        assert torch.equal(y.view(torch.int16), ref.view(torch.int16))
+    assert F.lib.cbnb_last_error() == 0

@@ -508,3 +508,48 @@ def test_linear8bitlt_loads_reference_format_checkpoint(F, fmt):
     with torch.no_grad():
         y1 = lin2(x)
     assert torch.equal(y0, y1)
+
+
+@pytest.mark.parametrize("has_fp16_weights", [False, True])
+@pytest.mark.parametrize("threshold", [0.0, 6.0])
+def test_matmul8bitlt_backward_vs_oracle(F, has_fp16_weights, threshold):
+    """MatMul8bitLt.backward against the oracle's restatement of reference _functions.py:436-483 (oracle.llm_int8_backward):
+    the int8 products are exact and mm_dequant has a fixed fp32 order, so grad_B and the int8-route grad_A are bit-exact
+    where no 16-bit side product is added; the 16-bit GEMMs (frozen-weight grad_A, outlier columns of grad_B) agree to
+    2 fp16 ulp of the magnitudes involved (fp32 summation order of the BLAS)."""
+    import bnb_b200
+    torch.manual_seed(17)
+    m, k, n = 96, 256, 128
+    W = (torch.randn(n, k) * 0.05).half()
+    x = torch.randn(m, k).half()
+    if threshold > 0:
+        x[:, 9] = 8.0
+        x[5, 100] = -7.5
+    lin = bnb_b200.nn.Linear8bitLt(k, n, bias=False, has_fp16_weights=has_fp16_weights, threshold=threshold)
+    lin.weight.data.copy_(W)
+    lin = lin.cuda().half()
+    lin.train()
+    xg = x.cuda().clone().requires_grad_(True)
+    y = lin(xg)
+    g = torch.randn(m, n).half()
+    y.backward(g.cuda())
+    torch.cuda.synchronize()
+    if has_fp16_weights:
+        gA, gB = orc.llm_int8_backward(g.numpy(), x.numpy(), threshold, W_f16=W.numpy(), need_grad_B=True)
+        got_B = lin.weight.grad.cpu().numpy()
+        idx = [9, 100] if threshold > 0 else []
+        clean = np.ones(k, bool)
+        clean[idx] = False
+        assert np.array_equal(got_B[:, clean].view(np.uint16), gB[:, clean].view(np.uint16))        # int8 route: bit-exact
+        if idx:
+            d = np.abs(got_B[:, idx].astype(np.float32) - gB[:, idx].astype(np.float32))
+            mag = np.maximum(np.abs(gB[:, idx].astype(np.float32)), np.abs(g.numpy().astype(np.float32)).T @ np.abs(x.numpy()[:, idx].astype(np.float32)) * 2.0 ** -3)
+            assert (d <= 2.01 * 2.0 ** -10 * np.maximum(mag, 2.0 ** -14)).all()
+        assert np.array_equal(xg.grad.cpu().numpy().view(np.uint16), gA.view(np.uint16))             # int8 route: bit-exact
+    else:
+        CB = lin.state.CB if lin.state.CB is not None else lin.state.CxB
+        gA, _ = orc.llm_int8_backward(g.numpy(), x.numpy(), threshold, CB=CB.cpu().numpy(), SCB=lin.state.SCB.cpu().numpy())
+        got = xg.grad.cpu().numpy().astype(np.float32)
+        scale = np.abs(g.numpy().astype(np.float32)) @ np.abs((CB.cpu().numpy().astype(np.float32) * lin.state.SCB.cpu().numpy()[:, None] / 127.0))
+        assert (np.abs(got - gA.astype(np.float32)) <= 2.0 ** -10 * np.maximum(np.abs(gA.astype(np.float32)), scale * 2.0 ** -4) * 2.01 + 1e-7).all()
+        assert lin.weight.grad is None

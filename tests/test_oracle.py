@@ -319,3 +319,24 @@ def test_scalar_trees_match_reference_executed_vectors(tables):
     fp4 = np.array([orc.fp4_table()[i] * np.float32(0.73) for i in range(16)], np.float32)
     # dDequantizeFP4Tree multiplies (c * absmax) * sign left to right: the table at absmax 1 times 0.73 is the same product
     assert np.array_equal(fp4.view(np.uint32), g["deq_fp4_absmax0p73"].view(np.uint32))
+
+
+def test_llm_int8_backward_restatement_tracks_the_fp64_gradients():
+    """oracle.llm_int8_backward (reference _functions.py:436-483) on both weight modes: int8 quantisation noise only
+    against the exact gradients, and the outlier columns of grad_B carried in 16 bit."""
+    rng = np.random.RandomState(3)
+    m, k, n = 64, 128, 96
+    g = rng.randn(m, n).astype(np.float16)
+    x = rng.randn(m, k).astype(np.float16)
+    x[:, 7] = 8.0
+    W = (rng.randn(n, k) * 0.05).astype(np.float16)
+    gA, gB = orc.llm_int8_backward(g, x, 6.0, W_f16=W, need_grad_B=True)
+    ref_B = g.astype(np.float64).T @ x.astype(np.float64)
+    ref_A = g.astype(np.float64) @ W.astype(np.float64)
+    assert np.linalg.norm(gB - ref_B) / np.linalg.norm(ref_B) < 0.02
+    assert np.linalg.norm(gA - ref_A) / np.linalg.norm(ref_A) < 0.02
+    assert np.linalg.norm(gB[:, 7] - ref_B[:, 7]) / np.linalg.norm(ref_B[:, 7]) < 2e-3     # outlier column: 16-bit product
+    rs, cs, _ = orc.get_col_row_stats(W, 0.0)
+    CB, _, _, _, _ = orc.double_rowcol_quant(W, rs, cs)
+    gA2, none = orc.llm_int8_backward(g, x, 6.0, CB=CB, SCB=rs)
+    assert none is None and np.linalg.norm(gA2 - ref_A) / np.linalg.norm(ref_A) < 0.02
