@@ -348,8 +348,9 @@ def run_stack(args, workload, layers, full, world, rank, dev, sampler=None):
         peers.barrier()
         torch.cuda.synchronize()
         ok = True
+        x_of = {p: (g[0] if fuse_sharded else p) for g in groups for p in g}    # a fused group reads the x of its first linear
         for i, (qf, stf) in enumerate(full_first):
-            ref = F.gemv_4bit(xs[i], qf.t(), state=stf)
+            ref = F.gemv_4bit(xs[x_of[i]], qf.t(), state=stf)
             ok = ok and torch.equal(ref.view(torch.int16), peers.full(i).view(torch.int16))
         flag = torch.tensor([1 if ok else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
