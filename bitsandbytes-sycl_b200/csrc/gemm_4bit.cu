@@ -191,9 +191,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_gemm4_tcgen05(const __grid_cons
       const uint32_t wp = wring_s + wslot * kStageW + r * 32;
       const uint4 w0 = lds128(wp), w1 = lds128(wp + 16);
       const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-      asm volatile("" ::"r"(w[0]), "r"(w[4]) : "memory");   // the loads have completed before the slot is released
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tc::smem_u32(emptyW + wslot));
+      // the slot is handed back after the stage has been written (every dequantised value consumes the loaded
+      // registers, so both loads have returned by then) -- see the note in gemm_4bit_small.cuh
+      const uint32_t wbar = tc::smem_u32(emptyW + wslot);
       wslot += G;
       while (wslot >= a.wslots) { wslot -= a.wslots; wphase ^= 1u; }
 
@@ -213,7 +213,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_gemm4_tcgen05(const __grid_cons
       }
       tc::fence_proxy_async();                            // generic-proxy stores -> visible to the UMMA (async proxy)
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tc::smem_u32(fullA + stage));
+      if (lane == 0) {
+        tc::mbar_arrive(wbar);
+        tc::mbar_arrive(tc::smem_u32(fullA + stage));
+      }
       stage += G;
       while (stage >= a.stages) { stage -= a.stages; phase ^= 1u; }
     }
@@ -294,6 +297,8 @@ static float *workspace(int dev, size_t bytes, cudaStream_t st, bool *from_pool)
 
 static int ilog2_(int v) { int s = 0; while ((1 << s) < v) s++; return s; }
 
+#include "gemm_4bit_small.cuh"
+
 // returns 0 ok, 1 shape not taken by the fused kernel (caller uses dequantize + matmul), 2 error
 template <typename T>
 int gemm_4bit(int batch, int N, int K, const T *A, const unsigned char *B, const float *absmax, const float *datatype,
@@ -312,6 +317,10 @@ int gemm_4bit(int batch, int N, int K, const T *A, const unsigned char *B, const
   static int num_sms[64] = {0};
   if (!num_sms[dev]) cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
   cudaStream_t st = current_stream();
+  static int small_off = -1;
+  if (small_off < 0) { const char *e = getenv("BNB_B200_GEMM4_SMALL"); small_off = (e && e[0] == '0') ? 1 : 0; }
+  if (batch <= 64 && !small_off && K / TK >= 8)
+    return gemm_4bit_small<T>(batch, N, K, A, B, absmax, datatype, bias, out, ilog2_(blocksize), num_sms[dev], dev, st);
 
   Args a{};
   a.batch = batch; a.N = N; a.K = K; a.blocksize = blocksize; a.bs_shift = ilog2_(blocksize);
@@ -320,11 +329,18 @@ int gemm_4bit(int batch, int N, int K, const T *A, const unsigned char *B, const
   const int stage_bytes = kStageA + a.NB * 128;
   a.stages = kDqWarps / 4;                                 // one operand stage per dequant group (the groups' ring
                                                            // arithmetic needs stages >= groups)
-  bool two_cta = a.NB <= 64;                               // two CTAs per SM while the activation tile is small
-  a.wslots = ((two_cta ? 110 : 220) * 1024 - 2048 - a.stages * stage_bytes) / kStageW;
-  if (two_cta && a.wslots < a.stages + 1) { two_cta = false; a.wslots = (220 * 1024 - 2048 - a.stages * stage_bytes) / kStageW; }
+  // ONE CTA per SM.  The packed-weight ring must hold a MULTIPLE of the group count of slots, so that a slot is always
+  // drained by the same dequant group: TMA loads complete out of order, and a group waiting for round r + 1 of a slot
+  // whose round r another group has not seen yet falls through the parity test (the phase two back has the same parity)
+  // and dequantises the previous round's bytes.  Round 1's two-CTAs-per-SM configuration had 13 slots for 4 groups and
+  // returned wrong results whenever the weights were not already in L2 (tools/gemm4_stress.py: 37 / 40 launches after
+  // an L2 flush); its tests always ran on freshly written, L2-resident weights.  Batch <= 64 now takes k_gemm4_small,
+  // this kernel keeps batch 65..256 and the shapes the small kernel refuses.
+  const bool two_cta = false;
+  a.wslots = (220 * 1024 - 2048 - a.stages * stage_bytes) / kStageW;
   if (a.wslots > kMaxWSlots) a.wslots = kMaxWSlots;
-  if (a.wslots < a.stages + 1) return 1;
+  a.wslots -= a.wslots % (kDqWarps / 4);
+  if (a.wslots < a.stages) return 1;
   const int tiles = (N + TM - 1) / TM;
   const int target = num_sms[dev] * (two_cta ? 2 : 1);
   int splits = target / tiles;

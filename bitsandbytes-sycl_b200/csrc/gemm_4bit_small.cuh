@@ -1,0 +1,370 @@
+// gemm_4bit_small.cuh -- batch 9..64 route of the fused 4-bit GEMM (included by gemm_4bit.cu).
+//
+// The general kernel (k_gemm4_tcgen05) dequantises every weight with the reference's arithmetic -- two table lookups,
+// two fp32 multiplies by absmax, one conversion per packed byte -- and at batch <= 64, where the tile is HBM-bound, those
+// ~9 thread-instructions per weight are the whole cost (ncu: issue 47 %, tensor pipe 3 %).  Here the per-block scale
+// leaves the per-weight path:
+//   * the UMMA A operand is the UNSCALED code value T(code[q]): one PRMT + one conflict-free LDS per packed byte out of
+//     the lane-replicated byte-pair table of the GEMV, one STS.128 per eight weights (~1.2 instructions per weight);
+//   * a stage is exactly one quantisation block of every row (64 k-elements, blocksize 64; a larger blocksize spans
+//     whole stages), accumulated by four tcgen05.mma into its OWN slot of a ring of TMEM accumulators;
+//   * four "scaler" warps (thread = TMEM lane = weight row) lift a finished slot out of TMEM, multiply it by the fp32
+//     absmax of (row, block) and add it to fp32 totals kept in registers: batch FMAs per row per block instead of 64
+//     multiplies -- and code * absmax is never rounded to T, so the result is closer to the exact product than the
+//     reference's dequantize-then-matmul (tests compare with both).
+// Persistent CTAs (one per SM) walk (128-row tile, K split) units; split-K partials go to the fp32 workspace of the
+// general kernel and are summed by k_gemm4_finalize in split order.
+#pragma once
+
+namespace g4s {
+constexpr int TM = 128, TK = 64;
+constexpr int kStageA = TM * 128;          // 16 KB: 128 rows x 64 T, SWIZZLE_128B
+constexpr int kStageW = TM * 32;           // 4 KB of packed weights
+constexpr int kDqGroups = 3;               // dequant groups of four warps; group g fills stages g, g + 3, ...
+// packed-weight ring.  A multiple of the group count, so that a slot is always drained by the SAME group: TMA loads
+// complete out of order, and a group that waited for round r + 1 of a slot another group has not yet seen round r of
+// would fall through the parity test (the phase two back has the same parity) and read the previous round's bytes.
+constexpr int kWSlots = 9;
+static_assert(kWSlots % kDqGroups == 0, "a packed-weight slot must belong to one dequant group");
+constexpr int kDqWarps = 4 * kDqGroups;
+constexpr int kFirstDq = 4, kFirstSc = kFirstDq + kDqWarps;   // warps: 0 W-TMA | 1 MMA | 2 X-TMA | 3 - | dequant | 4 scalers
+constexpr int kThreads = (kFirstSc + 4) * 32;
+constexpr int kLut = 65536;                // byte-pair table, entry stride 256 B, one word per lane
+__host__ __device__ constexpr int stages_for(int NB) { return NB <= 32 ? 6 : 5; }   // operand ring == TMEM accumulator ring
+
+struct Args {
+  int batch, N, K, bs_shift;
+  int NB;            // UMMA N: batch rounded up to 16 (<= 64)
+  int splits, kper;  // K elements per split (multiple of 64)
+  int tiles;         // 128-row tiles
+  const unsigned char *B;
+  const float *absmax;
+  const float *code;
+  const void *bias;  // T[N] or null
+  void *out;         // T[batch, N]           (splits == 1)
+  float *ws;         // fp32 [splits, batch, N] (splits > 1)
+};
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+
+// explicit shared-space load: the table pointer is derived from the aligned dynamic-smem base, which the compiler would
+// otherwise treat as a generic address (LD instead of LDS)
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+
+// One mbarrier per operand stage collects EVERYTHING the MMA issuer needs for that stage -- the four dequant warps of
+// the group, the activation tile's TMA bytes, and the four scaler warps handing back the TMEM slot of the same index --
+// so the single issuing thread pays one wait per stage (a try_wait costs ~100 cycles even when it succeeds, and three of
+// them per 64-element stage were the critical path of the first version of this kernel).
+template <typename T, int NB16>   // NB16 = NB / 16 (1..4)
+__global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_constant__ CUtensorMap tmX,
+                                                           const __grid_constant__ CUtensorMap tmW, const Args a) {
+  constexpr int NB = NB16 * 16;
+  constexpr int S = stages_for(NB);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int stageB = NB * 128;
+  constexpr int stage_bytes = kStageA + stageB;
+  // [0, 64 KB) byte-pair table | operand ring | packed ring | barriers
+  uint8_t *ring = smem + kLut;
+  uint8_t *wring = ring + S * stage_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(wring + kWSlots * kStageW);
+  uint64_t *full = bars, *empty = bars + 8, *accfull = bars + 16, *fullW = bars + 24, *emptyW = bars + 24 + kWSlots;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24 + 2 * kWSlots);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int units = a.tiles * a.splits;
+
+  if (warp == 0 && lane == 0) tc::prefetch_tmap(&tmW);
+  if (warp == 2 && lane == 0) tc::prefetch_tmap(&tmX);
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < S; s++) {
+        tc::mbar_init(tc::smem_u32(full + s), 4 + 1 + 4);   // dequant warps + X expect_tx + scaler warps (TMEM slot free)
+        tc::mbar_init(tc::smem_u32(empty + s), 1);          // tcgen05.commit: shared-memory stage consumed
+        tc::mbar_init(tc::smem_u32(accfull + s), 1);        // tcgen05.commit: TMEM slot complete
+      }
+      for (int s = 0; s < kWSlots; s++) {
+        tc::mbar_init(tc::smem_u32(fullW + s), 1);
+        tc::mbar_init(tc::smem_u32(emptyW + s), 4);
+      }
+      tc::fence_barrier_init();
+    }
+    __syncwarp();
+    tc::tmem_alloc(tc::smem_u32(tmem_slot), 512);
+  }
+  if (warp >= kFirstDq && warp < kFirstSc) {
+    // byte-pair table e -> {T(code[e >> 4]), T(code[e & 15])}, replicated for the 32 lanes: 8 threads per entry
+    const int dt = threadIdx.x - kFirstDq * 32;
+    const int j8 = dt & 7;
+    for (int e = dt >> 3; e < 256; e += (kDqWarps * 32) / 8) {
+      const uint32_t v = (g4::pack2<T>(__ldg(a.code + (e >> 4)), 0.f) & 0xFFFFu) | (g4::pack2<T>(__ldg(a.code + (e & 15)), 0.f) << 16);
+      *reinterpret_cast<uint4 *>(smem + e * 256 + j8 * 16) = make_uint4(v, v, v, v);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto unit_range = [&](int u, int &tile, int &split, int &k_begin, int &nk) {
+    tile = u / a.splits;
+    split = u - tile * a.splits;
+    k_begin = split * a.kper;
+    const int k_end = min(a.K, k_begin + a.kper);
+    nk = (k_end - k_begin) / TK;
+  };
+
+  if (warp == 0) {
+    // ================= packed weights: TMA into the deep ring =================
+    if (lane == 0) {
+      int wslot = 0; uint32_t wphase = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        int tile, split, k_begin, nk;
+        unit_range(u, tile, split, k_begin, nk);
+        for (int i = 0; i < nk; i++) {
+          tc::mbar_wait(tc::smem_u32(emptyW + wslot), wphase ^ 1);
+          const uint32_t fw = tc::smem_u32(fullW + wslot);
+          tc::mbar_arrive_expect_tx(fw, kStageW);
+          tc::tma_load_2d(tc::smem_u32(wring + wslot * kStageW), &tmW, fw, (k_begin + i * TK) >> 1, tile * TM);
+          if (++wslot == kWSlots) { wslot = 0; wphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================= activations: TMA into the operand ring =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        int tile, split, k_begin, nk;
+        unit_range(u, tile, split, k_begin, nk);
+        for (int kb = 0; kb < nk; kb++) {
+          tc::mbar_wait(tc::smem_u32(empty + stage), phase ^ 1);
+          const uint32_t fb = tc::smem_u32(full + stage);
+          tc::mbar_arrive_expect_tx(fb, (uint32_t)stageB);
+          tc::tma_load_2d(tc::smem_u32(ring + stage * stage_bytes + kStageA), &tmX, fb, k_begin + kb * TK, 0);
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: four k16 steps per stage into the TMEM slot of the same index =================
+    if (lane == 0) {
+      const uint32_t idesc = tc::umma_idesc(tc::kCFormatF32, std::is_same<T, __nv_bfloat16>::value ? 1u : 0u, TM, (uint32_t)NB);
+      int stage = 0; uint32_t phase = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        int tile, split, k_begin, nk;
+        unit_range(u, tile, split, k_begin, nk);
+        for (int kb = 0; kb < nk; kb++) {
+          tc::mbar_wait(tc::smem_u32(full + stage), phase);
+          tc::fence_after_sync();
+          const uint32_t sa = tc::smem_u32(ring + stage * stage_bytes);
+          const uint64_t adesc = tc::umma_desc_sw128_kmajor(sa);
+          const uint64_t bdesc = tc::umma_desc_sw128_kmajor(sa + kStageA);
+#pragma unroll
+          for (int k = 0; k < TK / 16; k++)
+            tc::umma_f16(tmem_base + (uint32_t)(stage * NB), adesc + 2 * k, bdesc + 2 * k, idesc, k != 0);
+          tc::umma_commit(tc::smem_u32(empty + stage));
+          tc::umma_commit(tc::smem_u32(accfull + stage));
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= kFirstDq && warp < kFirstSc) {
+    // ================= dequant producers: packed bytes -> unscaled T(code) pairs =================
+    constexpr int G = kDqGroups;
+    const int dt = threadIdx.x - kFirstDq * 32;
+    const int r = dt & 127;                               // weight row inside the tile
+    const int grp = dt >> 7;
+    const uint32_t swz = (uint32_t)(r & 7);
+    const uint32_t lane4 = (uint32_t)(lane * 4);
+    const uint32_t ring_s = tc::smem_u32(ring), wring_s = tc::smem_u32(wring), smem_s = tc::smem_u32(smem);
+    int stage = grp % S, wslot = grp % kWSlots;
+    uint32_t phase = (uint32_t)(grp / S) & 1u, wphase = (uint32_t)(grp / kWSlots) & 1u;
+    int total = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      int tile, split, k_begin, nk;
+      unit_range(u, tile, split, k_begin, nk);
+      total += nk;
+    }
+    for (int it = grp; it < total; it += G) {
+      tc::mbar_wait(tc::smem_u32(fullW + wslot), wphase);
+      const uint32_t wp = wring_s + wslot * kStageW + r * 32;
+      const uint4 w0 = g4::lds128(wp), w1 = g4::lds128(wp + 16);
+      const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      // The slot is handed back AFTER the stage has been written (below), not here: every table lookup consumes the
+      // loaded registers, so by then both loads have returned.  An arrive issued right behind the LDS.128 (what this code
+      // did first; an empty inline asm naming the registers does not make ptxas wait on the load scoreboard) let the
+      // next round's TMA bytes land in rows a warp had not read yet -- seen only with cold caches, as a handful of rows
+      // of one tile computed with the weights of the stage nine further on.
+      const uint32_t wbar = tc::smem_u32(emptyW + wslot);
+      wslot += G;
+      while (wslot >= kWSlots) { wslot -= kWSlots; wphase ^= 1u; }
+
+      tc::mbar_wait(tc::smem_u32(empty + stage), phase ^ 1);
+      const uint32_t dst = ring_s + stage * stage_bytes + r * 128;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {                       // one packed word = 8 elements = one 16-byte chunk
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)                       // byte i of the word: even element in the high nibble = low half of the pair
+          o[i] = lds32(smem_s + __byte_perm(w[c], lane4, 0x7604u | (i << 4)));
+        g4::sts128(dst + (((uint32_t)c ^ swz) << 4), o[0], o[1], o[2], o[3]);
+      }
+      tc::fence_proxy_async();                            // generic-proxy stores -> visible to the UMMA (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        tc::mbar_arrive(wbar);
+        tc::mbar_arrive(tc::smem_u32(full + stage));
+      }
+      stage += G;
+      while (stage >= S) { stage -= S; phase ^= 1u; }
+    }
+  } else if (warp >= kFirstSc) {
+    // ================= scalers: TMEM slot * absmax(row, block) -> fp32 totals; epilogue per unit =================
+    const int q = warp & 3;                               // TMEM lane quarter of this warp
+    const int r = q * 32 + lane;
+    if (lane == 0)                                        // round 0: every TMEM slot starts free
+      for (int s = 0; s < S; s++) tc::mbar_arrive(tc::smem_u32(full + s));
+    int stage = 0; uint32_t phase = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      int tile, split, k_begin, nk;
+      unit_range(u, tile, split, k_begin, nk);
+      const int orow = tile * TM + r;
+      const int row = min(orow, a.N - 1);
+      const size_t ebase = (size_t)row * a.K + k_begin;
+      float tot[NB];
+#pragma unroll
+      for (int j = 0; j < NB; j++) tot[j] = 0.f;
+      float am_next = __ldg(a.absmax + (ebase >> a.bs_shift));
+      for (int kb = 0; kb < nk; kb++) {
+        const float am = am_next;
+        if (kb + 1 < nk) am_next = __ldg(a.absmax + ((ebase + (size_t)(kb + 1) * TK) >> a.bs_shift));
+        tc::mbar_wait(tc::smem_u32(accfull + stage), phase);
+        tc::fence_after_sync();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * NB);
+        if (NB16 <= 2) {      // lift the whole slot, hand it back, then scale (registers allow it)
+          uint32_t v[NB16][16];
+#pragma unroll
+          for (int c = 0; c < NB16; c++) tmem_ld_32x32b_x16(taddr + c * 16, v[c]);
+          tc::tmem_ld_wait();
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(tc::smem_u32(full + stage));   // the slot may be overwritten by this stage's next round
+#pragma unroll
+          for (int c = 0; c < NB16; c++)
+#pragma unroll
+            for (int j = 0; j < 16; j++) tot[c * 16 + j] = __fmaf_rn(__uint_as_float(v[c][j]), am, tot[c * 16 + j]);
+        } else {              // 48 / 64 columns: 16 at a time
+#pragma unroll
+          for (int c = 0; c < NB16; c++) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(taddr + c * 16, v);
+            tc::tmem_ld_wait();
+            if (c == NB16 - 1) {
+              tc::fence_before_sync();
+              __syncwarp();
+              if (lane == 0) tc::mbar_arrive(tc::smem_u32(full + stage));
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j++) tot[c * 16 + j] = __fmaf_rn(__uint_as_float(v[j]), am, tot[c * 16 + j]);
+          }
+        }
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+      if (orow < a.N) {
+        float bias = 0.f;
+        if (a.bias != nullptr && a.splits == 1) bias = to_float<T>(reinterpret_cast<const T *>(a.bias)[orow]);
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+          if (b < a.batch) {
+            if (a.splits == 1) reinterpret_cast<T *>(a.out)[(size_t)b * a.N + orow] = from_float<T>(__fadd_rn(tot[b], bias));
+            else a.ws[((size_t)split * a.batch + b) * a.N + orow] = tot[b];
+          }
+        }
+      }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+}
+
+constexpr size_t smem_bytes(int NB) {
+  return (size_t)kLut + (size_t)stages_for(NB) * (kStageA + NB * 128) + (size_t)kWSlots * kStageW + 1024 /*align*/ + 512 /*barriers*/;
+}
+}  // namespace g4s
+
+// host: batch 9..64.  returns 0 ok, 1 not taken, 2 error
+template <typename T>
+static int gemm_4bit_small(int batch, int N, int K, const T *A, const unsigned char *B, const float *absmax, const float *datatype,
+                           const T *bias, T *out, int bs_shift, int sms, int dev, cudaStream_t st) {
+  using namespace g4s;
+  Args a{};
+  a.batch = batch; a.N = N; a.K = K; a.bs_shift = bs_shift;
+  a.NB = (batch + 15) / 16 * 16;
+  a.B = B; a.absmax = absmax; a.code = datatype; a.bias = bias; a.out = out;
+  a.tiles = (N + TM - 1) / TM;
+  // K splits: the makespan of `units` equal units on `sms` persistent CTAs, each unit = its stages + ~6 stages of fill /
+  // drain / epilogue; at least 8 stages per unit
+  const int kblocks = K / TK;
+  int best = 1;
+  long best_cost = -1;
+  for (int s = 1; s <= 16 && kblocks / s >= 8; s++) {
+    const int kb_per = (kblocks + s - 1) / s;
+    const int ns = (kblocks + kb_per - 1) / kb_per;
+    const long waves = ((long)a.tiles * ns + sms - 1) / sms;
+    const long cost = waves * (kb_per + 6);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+  }
+  const int kb_per = (kblocks + best - 1) / best;
+  a.kper = kb_per * TK;
+  a.splits = (kblocks + kb_per - 1) / kb_per;
+  bool ws_from_pool = false;
+  if (a.splits > 1) {
+    a.ws = g4::workspace(dev, (size_t)a.splits * batch * N * sizeof(float), st, &ws_from_pool);
+    if (a.ws == nullptr) { a.splits = 1; a.kper = K; }
+  }
+  CUtensorMap tmX, tmW;
+  if (!make_tmap_2d(&tmX, A, 2, (uint64_t)batch, (uint64_t)K, (uint32_t)a.NB, TK, true, std::is_same<T, __nv_bfloat16>::value) ||
+      !make_tmap_2d(&tmW, B, 1, (uint64_t)N, (uint64_t)(K / 2), TM, TK / 2, false, false, false)) {
+    if (ws_from_pool) cudaFreeAsync(a.ws, st);
+    return 2;
+  }
+  const int units = a.tiles * a.splits;
+  const int grid = units < sms ? units : sms;
+  const size_t smem = smem_bytes(a.NB);
+#define G4S_LAUNCH(NB16_)                                                                                                 \
+  do {                                                                                                                  \
+    auto kfn = k_gemm4_small<T, NB16_>;                                                                                 \
+    ensure_max_dynamic_smem(reinterpret_cast<const void *>(kfn), (int)smem_bytes(NB16_ * 16), "gemm_4bit small smem attr"); \
+    kfn<<<grid, kThreads, smem, st>>>(tmX, tmW, a);                                                                     \
+  } while (0)
+  switch (a.NB / 16) {
+    case 1: G4S_LAUNCH(1); break;
+    case 2: G4S_LAUNCH(2); break;
+    case 3: G4S_LAUNCH(3); break;
+    default: G4S_LAUNCH(4); break;
+  }
+#undef G4S_LAUNCH
+  check_launch("gemm_4bit (small batch, tcgen05)");
+  if (a.splits > 1) {
+    const size_t total = (size_t)batch * N;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > sms * 8) blocks = sms * 8;
+    g4::k_gemm4_finalize<T><<<blocks, 256, 0, st>>>(a.ws, bias, out, a.splits, batch, N);
+    check_launch("gemm_4bit (finalize)");
+    if (ws_from_pool) cudaFreeAsync(a.ws, st);
+  }
+  return 0;
+}
