@@ -18,7 +18,6 @@
 
 namespace g4s {
 constexpr int TM = 128, TK = 64;
-constexpr int kStageA = TM * 128;          // 16 KB: 128 rows x 64 T, SWIZZLE_128B
 constexpr int kStageW = TM * 32;           // 4 KB of packed weights
 constexpr int kDqGroups = 3;               // dequant groups of four warps; group g fills stages g, g + 3, ...
 // packed-weight ring.  A multiple of the group count, so that a slot is always drained by the SAME group: TMA loads
@@ -43,6 +42,9 @@ struct Args {
   const void *bias;  // T[N] or null
   void *out;         // T[batch, N]           (splits == 1)
   float *ws;         // fp32 [splits, batch, N] (splits > 1)
+#ifdef G4S_TRACE
+  int dbg;           // trace build only: 1 skip the dequant work, 2 skip the MMAs, 4 skip the TMEM loads
+#endif
 };
 
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -53,6 +55,24 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
       : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+        "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+        "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: A is read from tensor memory -- row i in lane i, two 16-bit elements per column, eight
+// columns per k16 step -- so the operand the dequant warps produce never goes through shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+               ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // explicit shared-space load: the table pointer is derived from the aligned dynamic-smem base, which the compiler would
 // otherwise treat as a generic address (LD instead of LDS)
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
@@ -60,6 +80,18 @@ __device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
   asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
   return v;
 }
+
+#ifdef G4S_TRACE
+#define G4S_T0() const long long t_role0 = clock64(); long long t_w0 = 0, t_w1 = 0, t_w2 = 0
+#define G4S_WAIT(acc, bar, par) do { const long long t_ = clock64(); tc::mbar_wait(bar, par); acc += clock64() - t_; } while (0)
+#define G4S_DBG(bit) (a.dbg & (bit))
+#define G4S_REPORT(name, cond) do { if (blockIdx.x == 5 && (cond)) printf("g4s %-8s warp %2d: total %lld wait0 %lld wait1 %lld wait2 %lld\n", name, (int)(threadIdx.x >> 5), clock64() - t_role0, t_w0, t_w1, t_w2); } while (0)
+#else
+#define G4S_T0() do {} while (0)
+#define G4S_DBG(bit) false
+#define G4S_WAIT(acc, bar, par) tc::mbar_wait(bar, par)
+#define G4S_REPORT(name, cond) do {} while (0)
+#endif
 
 // One mbarrier per operand stage collects EVERYTHING the MMA issuer needs for that stage -- the four dequant warps of
 // the group, the activation tile's TMA bytes, and the four scaler warps handing back the TMEM slot of the same index --
@@ -72,14 +104,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_consta
   constexpr int S = stages_for(NB);
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int stageB = NB * 128;
-  constexpr int stage_bytes = kStageA + stageB;
-  // [0, 64 KB) byte-pair table | operand ring | packed ring | barriers
+  constexpr int stageB = NB * 128;           // activation tile: NB rows x 64 T, SWIZZLE_128B
+  constexpr uint32_t kAccCols = S * NB;      // TMEM: S accumulator slots of NB columns, then S weight stages of 32 columns
+  // [0, 64 KB) byte-pair table | activation ring | packed ring | barriers
   uint8_t *ring = smem + kLut;
-  uint8_t *wring = ring + S * stage_bytes;
+  uint8_t *wring = ring + S * stageB;
   uint64_t *bars = reinterpret_cast<uint64_t *>(wring + kWSlots * kStageW);
-  uint64_t *full = bars, *empty = bars + 8, *accfull = bars + 16, *fullW = bars + 24, *emptyW = bars + 24 + kWSlots;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24 + 2 * kWSlots);
+  uint64_t *full = bars, *done = bars + 8, *fullW = bars + 16, *emptyW = bars + 16 + kWSlots;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16 + 2 * kWSlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int units = a.tiles * a.splits;
@@ -90,8 +122,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_consta
     if (lane == 0) {
       for (int s = 0; s < S; s++) {
         tc::mbar_init(tc::smem_u32(full + s), 4 + 1 + 4);   // dequant warps + X expect_tx + scaler warps (TMEM slot free)
-        tc::mbar_init(tc::smem_u32(empty + s), 1);          // tcgen05.commit: shared-memory stage consumed
-        tc::mbar_init(tc::smem_u32(accfull + s), 1);        // tcgen05.commit: TMEM slot complete
+        tc::mbar_init(tc::smem_u32(done + s), 1);           // tcgen05.commit: operands consumed AND accumulator slot complete
       }
       for (int s = 0; s < kWSlots; s++) {
         tc::mbar_init(tc::smem_u32(fullW + s), 1);
@@ -126,58 +157,76 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_consta
 
   if (warp == 0) {
     // ================= packed weights: TMA into the deep ring =================
-    if (lane == 0) {
+    // The three single-issuer roles run their loops with the WHOLE warp (uniform control flow, uniform operands) and
+    // elect one lane only around the issuing instructions: inside `if (lane == 0)` the compiler has to assume divergence
+    // and wraps every UTMALDG / UTCHMMA / UTCBAR in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop, ~60 cycles apiece --
+    // with four MMAs and a commit per 64-element stage that loop WAS the critical path of this kernel.
+    {
       int wslot = 0; uint32_t wphase = 0;
+      G4S_T0();
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
         int tile, split, k_begin, nk;
         unit_range(u, tile, split, k_begin, nk);
         for (int i = 0; i < nk; i++) {
-          tc::mbar_wait(tc::smem_u32(emptyW + wslot), wphase ^ 1);
-          const uint32_t fw = tc::smem_u32(fullW + wslot);
-          tc::mbar_arrive_expect_tx(fw, kStageW);
-          tc::tma_load_2d(tc::smem_u32(wring + wslot * kStageW), &tmW, fw, (k_begin + i * TK) >> 1, tile * TM);
+          G4S_WAIT(t_w0, tc::smem_u32(emptyW + wslot), wphase ^ 1);
+          if (tc::elect_one()) {
+            const uint32_t fw = tc::smem_u32(fullW + wslot);
+            tc::mbar_arrive_expect_tx(fw, kStageW);
+            tc::tma_load_2d(tc::smem_u32(wring + wslot * kStageW), &tmW, fw, (k_begin + i * TK) >> 1, tile * TM);
+          }
+          __syncwarp();
           if (++wslot == kWSlots) { wslot = 0; wphase ^= 1; }
         }
       }
+      G4S_REPORT("W-TMA", lane == 0);
     }
   } else if (warp == 2) {
     // ================= activations: TMA into the operand ring =================
-    if (lane == 0) {
+    {
       int stage = 0; uint32_t phase = 0;
+      G4S_T0();
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
         int tile, split, k_begin, nk;
         unit_range(u, tile, split, k_begin, nk);
         for (int kb = 0; kb < nk; kb++) {
-          tc::mbar_wait(tc::smem_u32(empty + stage), phase ^ 1);
-          const uint32_t fb = tc::smem_u32(full + stage);
-          tc::mbar_arrive_expect_tx(fb, (uint32_t)stageB);
-          tc::tma_load_2d(tc::smem_u32(ring + stage * stage_bytes + kStageA), &tmX, fb, k_begin + kb * TK, 0);
+          G4S_WAIT(t_w0, tc::smem_u32(done + stage), phase ^ 1);
+          if (tc::elect_one()) {
+            const uint32_t fb = tc::smem_u32(full + stage);
+            tc::mbar_arrive_expect_tx(fb, (uint32_t)stageB);
+            tc::tma_load_2d(tc::smem_u32(ring + stage * stageB), &tmX, fb, k_begin + kb * TK, 0);
+          }
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
+      G4S_REPORT("X-TMA", lane == 0);
     }
   } else if (warp == 1) {
     // ================= MMA issuer: four k16 steps per stage into the TMEM slot of the same index =================
-    if (lane == 0) {
+    {
       const uint32_t idesc = tc::umma_idesc(tc::kCFormatF32, std::is_same<T, __nv_bfloat16>::value ? 1u : 0u, TM, (uint32_t)NB);
       int stage = 0; uint32_t phase = 0;
+      G4S_T0();
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
         int tile, split, k_begin, nk;
         unit_range(u, tile, split, k_begin, nk);
         for (int kb = 0; kb < nk; kb++) {
-          tc::mbar_wait(tc::smem_u32(full + stage), phase);
+          G4S_WAIT(t_w0, tc::smem_u32(full + stage), phase);
           tc::fence_after_sync();
-          const uint32_t sa = tc::smem_u32(ring + stage * stage_bytes);
-          const uint64_t adesc = tc::umma_desc_sw128_kmajor(sa);
-          const uint64_t bdesc = tc::umma_desc_sw128_kmajor(sa + kStageA);
+          const uint64_t bdesc = tc::umma_desc_sw128_kmajor(tc::smem_u32(ring + stage * stageB));
+          const uint32_t ta = tmem_base + kAccCols + (uint32_t)(stage * 32);   // weights: 8 columns per k16 step
+          if (tc::elect_one()) {                               // the same lane every time (commit tracks the issuing thread)
+            if (!G4S_DBG(2))
 #pragma unroll
-          for (int k = 0; k < TK / 16; k++)
-            tc::umma_f16(tmem_base + (uint32_t)(stage * NB), adesc + 2 * k, bdesc + 2 * k, idesc, k != 0);
-          tc::umma_commit(tc::smem_u32(empty + stage));
-          tc::umma_commit(tc::smem_u32(accfull + stage));
+            for (int k = 0; k < TK / 16; k++)
+              umma_f16_ts(tmem_base + (uint32_t)(stage * NB), ta + 8 * k, bdesc + 2 * k, idesc, k != 0);
+            tc::umma_commit(tc::smem_u32(done + stage));
+          }
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
+      G4S_REPORT("MMA", lane == 0);
     }
   } else if (warp >= kFirstDq && warp < kFirstSc) {
     // ================= dequant producers: packed bytes -> unscaled T(code) pairs =================
@@ -185,9 +234,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_consta
     const int dt = threadIdx.x - kFirstDq * 32;
     const int r = dt & 127;                               // weight row inside the tile
     const int grp = dt >> 7;
-    const uint32_t swz = (uint32_t)(r & 7);
     const uint32_t lane4 = (uint32_t)(lane * 4);
-    const uint32_t ring_s = tc::smem_u32(ring), wring_s = tc::smem_u32(wring), smem_s = tc::smem_u32(smem);
+    const uint32_t wring_s = tc::smem_u32(wring), smem_s = tc::smem_u32(smem);
+    // TMEM lanes of this warp (a warp reaches lanes 32 * (warp % 4) ..., and row r = 32 * (warp % 4) + lane)
+    const uint32_t ta_warp = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kAccCols;
     int stage = grp % S, wslot = grp % kWSlots;
     uint32_t phase = (uint32_t)(grp / S) & 1u, wphase = (uint32_t)(grp / kWSlots) & 1u;
     int total = 0;
@@ -196,8 +246,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_consta
       unit_range(u, tile, split, k_begin, nk);
       total += nk;
     }
+    G4S_T0();
     for (int it = grp; it < total; it += G) {
-      tc::mbar_wait(tc::smem_u32(fullW + wslot), wphase);
+      G4S_WAIT(t_w0, tc::smem_u32(fullW + wslot), wphase);
       const uint32_t wp = wring_s + wslot * kStageW + r * 32;
       const uint4 w0 = g4::lds128(wp), w1 = g4::lds128(wp + 16);
       const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
@@ -210,17 +261,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_consta
       wslot += G;
       while (wslot >= kWSlots) { wslot -= kWSlots; wphase ^= 1u; }
 
-      tc::mbar_wait(tc::smem_u32(empty + stage), phase ^ 1);
-      const uint32_t dst = ring_s + stage * stage_bytes + r * 128;
+      G4S_WAIT(t_w1, tc::smem_u32(done + stage), phase ^ 1);
+      tc::fence_after_sync();
+      uint32_t o[32];                                     // word m = elements 2m (low half), 2m + 1 of this row's 64
+      if (!G4S_DBG(1))
 #pragma unroll
-      for (int c = 0; c < 8; c++) {                       // one packed word = 8 elements = one 16-byte chunk
-        uint32_t o[4];
+      for (int c = 0; c < 8; c++)                         // one packed word = 8 elements
 #pragma unroll
         for (int i = 0; i < 4; i++)                       // byte i of the word: even element in the high nibble = low half of the pair
-          o[i] = lds32(smem_s + __byte_perm(w[c], lane4, 0x7604u | (i << 4)));
-        g4::sts128(dst + (((uint32_t)c ^ swz) << 4), o[0], o[1], o[2], o[3]);
-      }
-      tc::fence_proxy_async();                            // generic-proxy stores -> visible to the UMMA (async proxy)
+          o[c * 4 + i] = lds32(smem_s + __byte_perm(w[c], lane4, 0x7604u | (i << 4)));
+      tmem_st_32x32b_x32(ta_warp + (uint32_t)(stage * 32), o);
+      tmem_st_wait();
+      tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) {
         tc::mbar_arrive(wbar);
@@ -229,6 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_consta
       stage += G;
       while (stage >= S) { stage -= S; phase ^= 1u; }
     }
+    G4S_REPORT("dequant", lane == 0);
   } else if (warp >= kFirstSc) {
     // ================= scalers: TMEM slot * absmax(row, block) -> fp32 totals; epilogue per unit =================
     const int q = warp & 3;                               // TMEM lane quarter of this warp
@@ -236,6 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_consta
     if (lane == 0)                                        // round 0: every TMEM slot starts free
       for (int s = 0; s < S; s++) tc::mbar_arrive(tc::smem_u32(full + s));
     int stage = 0; uint32_t phase = 0;
+    G4S_T0();
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       int tile, split, k_begin, nk;
       unit_range(u, tile, split, k_begin, nk);
@@ -249,11 +303,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_consta
       for (int kb = 0; kb < nk; kb++) {
         const float am = am_next;
         if (kb + 1 < nk) am_next = __ldg(a.absmax + ((ebase + (size_t)(kb + 1) * TK) >> a.bs_shift));
-        tc::mbar_wait(tc::smem_u32(accfull + stage), phase);
+        G4S_WAIT(t_w0, tc::smem_u32(done + stage), phase);
         tc::fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * NB);
         if (NB16 <= 2) {      // lift the whole slot, hand it back, then scale (registers allow it)
           uint32_t v[NB16][16];
+#pragma unroll
+          if (!G4S_DBG(4))
 #pragma unroll
           for (int c = 0; c < NB16; c++) tmem_ld_32x32b_x16(taddr + c * 16, v[c]);
           tc::tmem_ld_wait();
@@ -293,6 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_consta
         }
       }
     }
+    G4S_REPORT("scaler", lane == 0);
   }
 
   tc::fence_before_sync();
@@ -301,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_consta
 }
 
 constexpr size_t smem_bytes(int NB) {
-  return (size_t)kLut + (size_t)stages_for(NB) * (kStageA + NB * 128) + (size_t)kWSlots * kStageW + 1024 /*align*/ + 512 /*barriers*/;
+  return (size_t)kLut + (size_t)stages_for(NB) * (NB * 128) + (size_t)kWSlots * kStageW + 1024 /*align*/ + 512 /*barriers*/;
 }
 }  // namespace g4s
 
@@ -315,6 +372,9 @@ static int gemm_4bit_small(int batch, int N, int K, const T *A, const unsigned c
   a.NB = (batch + 15) / 16 * 16;
   a.B = B; a.absmax = absmax; a.code = datatype; a.bias = bias; a.out = out;
   a.tiles = (N + TM - 1) / TM;
+#ifdef G4S_TRACE
+  { const char *e = getenv("G4S_DBG"); a.dbg = e ? atoi(e) : 0; }
+#endif
   // K splits: the makespan of `units` equal units on `sms` persistent CTAs, each unit = its stages + ~6 stages of fill /
   // drain / epilogue; at least 8 stages per unit
   const int kblocks = K / TK;

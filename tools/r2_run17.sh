@@ -1,11 +1,11 @@
 #!/bin/bash
-# GPU session 16: W ring slot-to-group fix
-timeout 900 python -m pytest tests/test_gpu_gemm4.py -q -m gpu > gpurun_out/r16_t.log 2>&1; tail -6 gpurun_out/r16_t.log
+# GPU session 17: TMEM-resident weights operand, warp-uniform issue loops
+timeout 900 python -m pytest tests/test_gpu_gemm4.py -q -m gpu > gpurun_out/r17_t.log 2>&1; tail -6 gpurun_out/r17_t.log
 timeout 300 python tools/gemm4_stress.py 60 2>&1 | tail -6
-timeout 300 python tools/kbench.py --only gemm4 > gpurun_out/r16_kbench_gemm4.jsonl 2>&1
+timeout 300 python tools/kbench.py --only gemm4 > gpurun_out/r17_kbench_gemm4.jsonl 2>&1
 python - <<'PY'
 import json
-for l in open('gpurun_out/r16_kbench_gemm4.jsonl'):
+for l in open('gpurun_out/r17_kbench_gemm4.jsonl'):
     try: d=json.loads(l)
     except Exception: print(l.strip()[:200]); continue
     print(d['kernel'], d['us'], d.get('hbm_frac'), d.get('bf16_frac'), d.get('speedup_vs_composition'))
