@@ -19,17 +19,22 @@
 namespace g4s {
 constexpr int TM = 128, TK = 64;
 constexpr int kStageW = TM * 32;           // 4 KB of packed weights
-constexpr int kDqGroups = 3;               // dequant groups of four warps; group g fills stages g, g + 3, ...
+// dequant groups of four warps: group g fills stages g, g + 3, ...  (a fourth group, tried with an 8-deep stage ring,
+// bought nothing: profiles/r2_gemm4_small_roles.md)
+constexpr int kDqGroups = 3;
 // packed-weight ring.  A multiple of the group count, so that a slot is always drained by the SAME group: TMA loads
 // complete out of order, and a group that waited for round r + 1 of a slot another group has not yet seen round r of
 // would fall through the parity test (the phase two back has the same parity) and read the previous round's bytes.
-constexpr int kWSlots = 9;
+constexpr int kWSlots = 12;
 static_assert(kWSlots % kDqGroups == 0, "a packed-weight slot must belong to one dequant group");
 constexpr int kDqWarps = 4 * kDqGroups;
-constexpr int kFirstDq = 4, kFirstSc = kFirstDq + kDqWarps;   // warps: 0 W-TMA | 1 MMA | 2 X-TMA | 3 - | dequant | 4 scalers
-constexpr int kThreads = (kFirstSc + 4) * 32;
+constexpr int kFirstDq = 4, kFirstSc = kFirstDq + kDqWarps;   // warps: 0 W-TMA | 1 MMA even | 2 X-TMA | 3 MMA odd | dequant | scalers
+// scaler warps: one per TMEM lane quarter at NB = 16, two (each takes half of the accumulator columns) above
+__host__ __device__ constexpr int scaler_warps(int NB) { return NB <= 16 ? 4 : 8; }
+__host__ __device__ constexpr int threads_for(int NB) { return (kFirstSc + scaler_warps(NB)) * 32; }
 constexpr int kLut = 65536;                // byte-pair table, entry stride 256 B, one word per lane
-__host__ __device__ constexpr int stages_for(int NB) { return NB <= 32 ? 6 : 5; }   // operand ring == TMEM accumulator ring
+// stages = TMEM ring: S accumulator slots of NB columns + S weight stages of 32 columns <= 512 columns
+__host__ __device__ constexpr int stages_for(int NB) { return NB <= 48 ? 6 : 5; }
 
 struct Args {
   int batch, N, K, bs_shift;
@@ -55,6 +60,11 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
       : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -98,10 +108,11 @@ __device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
 // so the single issuing thread pays one wait per stage (a try_wait costs ~100 cycles even when it succeeds, and three of
 // them per 64-element stage were the critical path of the first version of this kernel).
 template <typename T, int NB16>   // NB16 = NB / 16 (1..4)
-__global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_constant__ CUtensorMap tmX,
+__global__ void __launch_bounds__(threads_for(NB16 * 16), 1) k_gemm4_small(const __grid_constant__ CUtensorMap tmX,
                                                            const __grid_constant__ CUtensorMap tmW, const Args a) {
   constexpr int NB = NB16 * 16;
   constexpr int S = stages_for(NB);
+  constexpr int G = kDqGroups, SCW = scaler_warps(NB);
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int stageB = NB * 128;           // activation tile: NB rows x 64 T, SWIZZLE_128B
@@ -121,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_consta
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < S; s++) {
-        tc::mbar_init(tc::smem_u32(full + s), 4 + 1 + 4);   // dequant warps + X expect_tx + scaler warps (TMEM slot free)
+        tc::mbar_init(tc::smem_u32(full + s), 4 + 1 + SCW);   // dequant warps + X expect_tx + scaler warps (TMEM slot free)
         tc::mbar_init(tc::smem_u32(done + s), 1);           // tcgen05.commit: operands consumed AND accumulator slot complete
       }
       for (int s = 0; s < kWSlots; s++) {
@@ -201,16 +212,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_consta
       }
       G4S_REPORT("X-TMA", lane == 0);
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer: four k16 steps per stage into the TMEM slot of the same index =================
+  } else if (warp == 1 || warp == 3) {
+    // ================= MMA issuers: four k16 steps per stage into the TMEM slot of the same index =================
+    // Two warps, alternate stages: every stage has its own accumulator slot, so MMAs of different stages need no order
+    // between them, and the ~350 cycles one thread spends per stage (wait, fence, issue, commit) run two abreast.
     {
+      const int mine = warp >> 1;                          // warp 1: even items, warp 3: odd items
+      int item = 0;
       const uint32_t idesc = tc::umma_idesc(tc::kCFormatF32, std::is_same<T, __nv_bfloat16>::value ? 1u : 0u, TM, (uint32_t)NB);
       int stage = 0; uint32_t phase = 0;
       G4S_T0();
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
         int tile, split, k_begin, nk;
         unit_range(u, tile, split, k_begin, nk);
-        for (int kb = 0; kb < nk; kb++) {
+        for (int kb = 0; kb < nk; kb++, item++) {
+          if ((item & 1) != mine) {
+            if (++stage == S) { stage = 0; phase ^= 1; }
+            continue;
+          }
           G4S_WAIT(t_w0, tc::smem_u32(full + stage), phase);
           tc::fence_after_sync();
           const uint64_t bdesc = tc::umma_desc_sw128_kmajor(tc::smem_u32(ring + stage * stageB));
@@ -230,7 +249,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_consta
     }
   } else if (warp >= kFirstDq && warp < kFirstSc) {
     // ================= dequant producers: packed bytes -> unscaled T(code) pairs =================
-    constexpr int G = kDqGroups;
     const int dt = threadIdx.x - kFirstDq * 32;
     const int r = dt & 127;                               // weight row inside the tile
     const int grp = dt >> 7;
@@ -263,6 +281,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_consta
 
       G4S_WAIT(t_w1, tc::smem_u32(done + stage), phase ^ 1);
       tc::fence_after_sync();
+#ifdef G4S_TRACE
+      const long long t_d0 = clock64();
+#endif
       uint32_t o[32];                                     // word m = elements 2m (low half), 2m + 1 of this row's 64
       if (!G4S_DBG(1))
 #pragma unroll
@@ -272,6 +293,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_consta
           o[c * 4 + i] = lds32(smem_s + __byte_perm(w[c], lane4, 0x7604u | (i << 4)));
       tmem_st_32x32b_x32(ta_warp + (uint32_t)(stage * 32), o);
       tmem_st_wait();
+#ifdef G4S_TRACE
+      t_w2 += clock64() - t_d0;
+#endif
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) {
@@ -285,6 +309,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_consta
   } else if (warp >= kFirstSc) {
     // ================= scalers: TMEM slot * absmax(row, block) -> fp32 totals; epilogue per unit =================
     const int q = warp & 3;                               // TMEM lane quarter of this warp
+    const int part = (warp - kFirstSc) >> 2;              // which part of the NB accumulator columns
+    constexpr int HC = NB / (SCW / 4);                    // columns (batch rows) this warp scales: 16, 24 or 32
+    const int col0 = part * HC;
     const int r = q * 32 + lane;
     if (lane == 0)                                        // round 0: every TMEM slot starts free
       for (int s = 0; s < S; s++) tc::mbar_arrive(tc::smem_u32(full + s));
@@ -296,55 +323,54 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm4_small(const __grid_consta
       const int orow = tile * TM + r;
       const int row = min(orow, a.N - 1);
       const size_t ebase = (size_t)row * a.K + k_begin;
-      float tot[NB];
+      float tot[HC];
 #pragma unroll
-      for (int j = 0; j < NB; j++) tot[j] = 0.f;
-      float am_next = __ldg(a.absmax + (ebase >> a.bs_shift));
+      for (int j = 0; j < HC; j++) tot[j] = 0.f;
+      // absmax of (row, block), two stages ahead
+      float am0 = __ldg(a.absmax + (ebase >> a.bs_shift));
+      float am1 = 1 < nk ? __ldg(a.absmax + ((ebase + (size_t)TK) >> a.bs_shift)) : 0.f;
       for (int kb = 0; kb < nk; kb++) {
-        const float am = am_next;
-        if (kb + 1 < nk) am_next = __ldg(a.absmax + ((ebase + (size_t)(kb + 1) * TK) >> a.bs_shift));
+        const float am = am0;
+        am0 = am1;
+        if (kb + 2 < nk) am1 = __ldg(a.absmax + ((ebase + (size_t)(kb + 2) * TK) >> a.bs_shift));
         G4S_WAIT(t_w0, tc::smem_u32(done + stage), phase);
         tc::fence_after_sync();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * NB);
-        if (NB16 <= 2) {      // lift the whole slot, hand it back, then scale (registers allow it)
-          uint32_t v[NB16][16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * NB + col0);
+        // lift this warp's columns, hand the slot back, then scale
+#ifdef G4S_TRACE
+        const long long t_s0 = clock64();
+#endif
+        uint32_t v[HC / 8][8];
+        if (!G4S_DBG(4))
 #pragma unroll
-          if (!G4S_DBG(4))
+        for (int c = 0; c < HC / 8; c++) tmem_ld_32x32b_x8(taddr + c * 8, v[c]);
+        tc::tmem_ld_wait();
+#ifdef G4S_TRACE
+        const long long t_s1 = clock64();
+        t_w1 += t_s1 - t_s0;
+#endif
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tc::smem_u32(full + stage));   // the slot may be overwritten by this stage's next round
 #pragma unroll
-          for (int c = 0; c < NB16; c++) tmem_ld_32x32b_x16(taddr + c * 16, v[c]);
-          tc::tmem_ld_wait();
-          tc::fence_before_sync();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(tc::smem_u32(full + stage));   // the slot may be overwritten by this stage's next round
+        for (int c = 0; c < HC / 8; c++)
 #pragma unroll
-          for (int c = 0; c < NB16; c++)
-#pragma unroll
-            for (int j = 0; j < 16; j++) tot[c * 16 + j] = __fmaf_rn(__uint_as_float(v[c][j]), am, tot[c * 16 + j]);
-        } else {              // 48 / 64 columns: 16 at a time
-#pragma unroll
-          for (int c = 0; c < NB16; c++) {
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(taddr + c * 16, v);
-            tc::tmem_ld_wait();
-            if (c == NB16 - 1) {
-              tc::fence_before_sync();
-              __syncwarp();
-              if (lane == 0) tc::mbar_arrive(tc::smem_u32(full + stage));
-            }
-#pragma unroll
-            for (int j = 0; j < 16; j++) tot[c * 16 + j] = __fmaf_rn(__uint_as_float(v[j]), am, tot[c * 16 + j]);
-          }
-        }
+          for (int j = 0; j < 8; j++) tot[c * 8 + j] = __fmaf_rn(__uint_as_float(v[c][j]), am, tot[c * 8 + j]);
+#ifdef G4S_TRACE
+        asm volatile("" ::"f"(tot[0]), "f"(tot[HC - 1]));
+        t_w2 += clock64() - t_s1;
+#endif
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
       if (orow < a.N) {
         float bias = 0.f;
         if (a.bias != nullptr && a.splits == 1) bias = to_float<T>(reinterpret_cast<const T *>(a.bias)[orow]);
 #pragma unroll
-        for (int b = 0; b < NB; b++) {
+        for (int j = 0; j < HC; j++) {
+          const int b = col0 + j;
           if (b < a.batch) {
-            if (a.splits == 1) reinterpret_cast<T *>(a.out)[(size_t)b * a.N + orow] = from_float<T>(__fadd_rn(tot[b], bias));
-            else a.ws[((size_t)split * a.batch + b) * a.N + orow] = tot[b];
+            if (a.splits == 1) reinterpret_cast<T *>(a.out)[(size_t)b * a.N + orow] = from_float<T>(__fadd_rn(tot[j], bias));
+            else a.ws[((size_t)split * a.batch + b) * a.N + orow] = tot[j];
           }
         }
       }
@@ -408,7 +434,7 @@ static int gemm_4bit_small(int batch, int N, int K, const T *A, const unsigned c
   do {                                                                                                                  \
     auto kfn = k_gemm4_small<T, NB16_>;                                                                                 \
     ensure_max_dynamic_smem(reinterpret_cast<const void *>(kfn), (int)smem_bytes(NB16_ * 16), "gemm_4bit small smem attr"); \
-    kfn<<<grid, kThreads, smem, st>>>(tmX, tmW, a);                                                                     \
+    kfn<<<grid, threads_for(NB16_ * 16), smem, st>>>(tmX, tmW, a);                                                                     \
   } while (0)
   switch (a.NB / 16) {
     case 1: G4S_LAUNCH(1); break;

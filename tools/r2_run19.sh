@@ -1,0 +1,14 @@
+#!/bin/bash
+# GPU session 19: four dequant groups, stage-split scalers at NB=16
+timeout 900 python -m pytest tests/test_gpu_gemm4.py -q -m gpu > gpurun_out/r19_t.log 2>&1; tail -6 gpurun_out/r19_t.log
+timeout 300 python tools/gemm4_stress.py 60 2>&1 | tail -6
+timeout 300 python tools/kbench.py --only gemm4 > gpurun_out/r19_kbench_gemm4.jsonl 2>&1
+python - <<'PY'
+import json
+for l in open('gpurun_out/r19_kbench_gemm4.jsonl'):
+    try: d=json.loads(l)
+    except Exception: print(l.strip()[:200]); continue
+    print(d['kernel'], d['us'], d.get('hbm_frac'), d.get('bf16_frac'), d.get('speedup_vs_composition'))
+PY
+timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -2
+timeout 120 python tools/gemm4_diag.py 2>&1 | tail -8
