@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(threads_for(NB16 * 16), 1) k_gemm4_small(const
       for (int kb = 0; kb < nk; kb++) {
         const float am = am0;
         am0 = am1;
-        if (kb + 2 < nk) am1 = __ldg(a.absmax + ((ebase + (size_t)(kb + 2) * TK) >> a.bs_shift));
+        if (kb + 2 < nk && !G4S_DBG(8)) am1 = __ldg(a.absmax + ((ebase + (size_t)(kb + 2) * TK) >> a.bs_shift));
         G4S_WAIT(t_w0, tc::smem_u32(done + stage), phase);
         tc::fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * NB + col0);
