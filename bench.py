@@ -575,6 +575,59 @@ def run_igemmlt_extras(steps, warmup):
     return out
 
 
+def run_gemm4_extras(steps, warmup):
+    """BASELINE config 4: fused NF4 GEMM, batch 16-256 on the Llama-3-8B MLP shape 14336x4096 (bf16, blocksize 64), through
+    `functional.gemm_4bit` (what `MatMul4Bit.forward` calls for batch > 1), beside the reference's composition
+    (`dequantize_4bit` + `F.linear`, _functions.py:490-518).  Six rotating copies of the packed weight (176 MB > L2), one
+    CUDA graph of six calls per measurement.  Rank 0, one GPU, outside the headline's timed region."""
+    import torch
+
+    from bnb_b200 import functional as F
+
+    peak_hbm, _ = measured_peak_gbs()
+    N, K = 14336, 4096
+    torch.manual_seed(5)
+    W = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
+    q, st = F.quantize_4bit(W, blocksize=64, compress_statistics=False, quant_type="nf4")
+    del W
+    qs = [q.clone() for _ in range(6)]
+    reps = max(5, min(20, steps))
+
+    def graph_us(fns):
+        def step():
+            for f in fns:
+                f()
+        run, graphed = _capture(step)
+        for _ in range(max(3, warmup)):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / (reps * len(fns)), graphed
+
+    out = {"config": "NF4 GEMM 14336x4096 bf16, blocksize 64 (BASELINE config 4)", "l2": "6 rotating weight copies, 176 MB > L2",
+           "api": "functional.gemm_4bit -> cgemm_4bit_bf16 (additive C-ABI entry)"}
+    with torch.no_grad():
+        for batch in (16, 32, 64, 256):
+            x = torch.randn(batch, K, device="cuda").bfloat16()
+            outs = [torch.empty(batch, N, dtype=torch.bfloat16, device="cuda") for _ in range(6)]
+            if F.gemm_4bit(x, qs[0].t(), st, out=outs[0]) is None:
+                out[f"batch{batch}"] = {"error": "fused kernel refused the shape"}
+                continue
+            us, graphed = graph_us([(lambda i=i: F.gemm_4bit(x, qs[i].t(), st, out=outs[i])) for i in range(6)])
+            us_ref, _ = graph_us([(lambda i=i: torch.nn.functional.linear(x, F.dequantize_4bit(qs[i], st))) for i in range(6)])
+            nbytes = N * K // 2 + 4 * N * K // 64 + 2 * batch * (K + N)
+            out[f"batch{batch}"] = {"us": us, "GBps": nbytes / us / 1e3, "hbm_frac": nbytes / us / 1e3 / peak_hbm,
+                                    "TFLOPs": 2.0 * batch * N * K / us / 1e6, "reference_composition_us": us_ref,
+                                    "speedup_vs_composition": us_ref / us, "launch": "cuda-graph" if graphed else "eager"}
+            del outs
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -585,7 +638,7 @@ def main():
     ap.add_argument("--workload", default="llama2-7b", choices=["llama2-7b", "llama3-70b"])
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the igemmlt and 70B-stack extra keys")
+    ap.add_argument("--no-extras", action="store_true", help="skip the igemmlt, gemm_4bit and 70B-stack extra keys")
     ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
                     help="N>1: output all-gather fused into the GEMV epilogue (peer stores), or one NCCL all-gather per linear")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph of the step")
@@ -640,6 +693,10 @@ def main():
                 extras["igemmlt"] = run_igemmlt_extras(args.steps, args.warmup)
             except Exception as e:  # noqa: BLE001
                 extras["igemmlt"] = {"error": f"{type(e).__name__}: {e}"}
+            try:
+                extras["gemm_4bit"] = run_gemm4_extras(args.steps, args.warmup)
+            except Exception as e:  # noqa: BLE001
+                extras["gemm_4bit"] = {"error": f"{type(e).__name__}: {e}"}
         if world > 1:
             dist.barrier()
 
