@@ -56,7 +56,7 @@ def test_library_is_sm100a_tensor_path():
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([exe, "-sass", LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    for mnemonic in ("UTCIMMA", "UTMALDG", "LDTM", "HMMA"):
+    for mnemonic in ("UTCIMMA", "UTCHMMA", "UTMALDG", "LDTM", "STTM", "HMMA"):
         assert mnemonic in sass, mnemonic
 
 
