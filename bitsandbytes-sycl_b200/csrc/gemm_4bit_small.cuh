@@ -18,28 +18,32 @@
 
 namespace g4s {
 constexpr int TM = 128, TK = 64;
-constexpr int kStageW = TM * 32;           // 4 KB of packed weights
+constexpr int kStageW = TM * 32;           // 4 KB of packed weights per quantisation block of the tile
 // dequant groups of four warps: group g fills stages g, g + 3, ...  (a fourth group, tried with an 8-deep stage ring,
 // bought nothing: profiles/r2_gemm4_small_roles.md)
 constexpr int kDqGroups = 3;
 // packed-weight ring.  A multiple of the group count, so that a slot is always drained by the SAME group: TMA loads
 // complete out of order, and a group that waited for round r + 1 of a slot another group has not yet seen round r of
 // would fall through the parity test (the phase two back has the same parity) and read the previous round's bytes.
-constexpr int kWSlots = 12;
-static_assert(kWSlots % kDqGroups == 0, "a packed-weight slot must belong to one dequant group");
+constexpr int kWBytes = 12 * 4096;           // packed-weight ring: 48 KB = 12 one-block or 6 two-block slots
+__host__ __device__ constexpr int wslots_for(int KB) { return kWBytes / (4096 * KB); }
+static_assert(wslots_for(1) % kDqGroups == 0 && wslots_for(2) % kDqGroups == 0, "a packed-weight slot must belong to one dequant group");
 constexpr int kDqWarps = 4 * kDqGroups;
 constexpr int kFirstDq = 4, kFirstSc = kFirstDq + kDqWarps;   // warps: 0 W-TMA | 1 MMA even | 2 X-TMA | 3 MMA odd | dequant | scalers
 // scaler warps: one per TMEM lane quarter at NB = 16, two (each takes half of the accumulator columns) above
 __host__ __device__ constexpr int scaler_warps(int NB) { return NB <= 16 ? 4 : 8; }
 __host__ __device__ constexpr int threads_for(int NB) { return (kFirstSc + scaler_warps(NB)) * 32; }
 constexpr int kLut = 65536;                // byte-pair table, entry stride 256 B, one word per lane
+constexpr int kBarBytes = 512;
+constexpr int kSmemBytes = 192 * 1024;     // rings below the second 64 KB boundary of the shared window, table above it
 // stages = TMEM ring: S accumulator slots of NB columns + S weight stages of 32 columns <= 512 columns
-__host__ __device__ constexpr int stages_for(int NB) { return NB <= 48 ? 6 : 5; }
+// (KB = quantisation blocks per barrier round: every role's wait -> work -> arrive round trip covers KB blocks)
+__host__ __device__ constexpr int stages_for(int NB, int KB) { return KB == 2 ? (NB <= 16 ? 5 : 4) : (NB <= 48 ? 6 : 5); }
 
 struct Args {
   int batch, N, K, bs_shift;
   int NB;            // UMMA N: batch rounded up to 16 (<= 64)
-  int splits, kper;  // K elements per split (multiple of 64)
+  int splits, kper;  // K elements per split (multiple of 64 * KB)
   int tiles;         // 128-row tiles
   const unsigned char *B;
   const float *absmax;
@@ -107,22 +111,31 @@ __device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
 // the group, the activation tile's TMA bytes, and the four scaler warps handing back the TMEM slot of the same index --
 // so the single issuing thread pays one wait per stage (a try_wait costs ~100 cycles even when it succeeds, and three of
 // them per 64-element stage were the critical path of the first version of this kernel).
-template <typename T, int NB16>   // NB16 = NB / 16 (1..4)
+template <typename T, int NB16, int KB>   // NB16 = NB / 16 (1..4); KB = 64-element blocks per round (2 only with NB <= 32)
 __global__ void __launch_bounds__(threads_for(NB16 * 16), 1) k_gemm4_small(const __grid_constant__ CUtensorMap tmX,
                                                            const __grid_constant__ CUtensorMap tmW, const Args a) {
   constexpr int NB = NB16 * 16;
-  constexpr int S = stages_for(NB);
+  constexpr int S = stages_for(NB, KB);
+  constexpr int kWSlots = wslots_for(KB);
+  constexpr int kSlotW = kStageW * KB;       // bytes of one packed-weight slot: 128 rows x 32 KB bytes
+  static_assert(S * KB * (NB + 32) <= 512, "TMEM columns");
   constexpr int G = kDqGroups, SCW = scaler_warps(NB);
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int stageB = NB * 128;           // activation tile: NB rows x 64 T, SWIZZLE_128B
-  constexpr uint32_t kAccCols = S * NB;      // TMEM: S accumulator slots of NB columns, then S weight stages of 32 columns
-  // [0, 64 KB) byte-pair table | activation ring | packed ring | barriers
-  uint8_t *ring = smem + kLut;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int tileB = NB * 128;            // activation tile of one block: NB rows x 64 T, SWIZZLE_128B
+  constexpr int stageB = tileB * KB;
+  constexpr uint32_t kAccCols = S * KB * NB; // TMEM: S x KB accumulator slots of NB columns, then S weight stages of 32 KB columns
+  // activation ring | packed ring | barriers | ... | byte-pair table at the next 64 KB boundary OF THE SHARED WINDOW: with
+  // bytes 0 and 1 of the table's address zero, one PRMT of (packed word, table | lane * 4) IS the lookup address -- no add
+  const uint32_t smem_base = tc::smem_u32(smem_raw);
+  const uint32_t ring_s0 = (smem_base + 1023u) & ~1023u;
+  const uint32_t lut_s = (ring_s0 + (uint32_t)(S * stageB + kWBytes + kBarBytes) + 0xFFFFu) & ~0xFFFFu;
+  if (lut_s + (uint32_t)kLut > smem_base + (uint32_t)kSmemBytes) __trap();   // shared window base moved: layout no longer fits
+  uint8_t *ring = smem_raw + (ring_s0 - smem_base);
   uint8_t *wring = ring + S * stageB;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(wring + kWSlots * kStageW);
-  uint64_t *full = bars, *done = bars + 8, *fullW = bars + 16, *emptyW = bars + 16 + kWSlots;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16 + 2 * kWSlots);
+  uint8_t *lut = smem_raw + (lut_s - smem_base);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(wring + kWBytes);
+  uint64_t *full = bars, *done = bars + 8, *fullW = bars + 16, *emptyW = bars + 16 + 12;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16 + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int units = a.tiles * a.splits;
@@ -150,7 +163,7 @@ __global__ void __launch_bounds__(threads_for(NB16 * 16), 1) k_gemm4_small(const
     const int j8 = dt & 7;
     for (int e = dt >> 3; e < 256; e += (kDqWarps * 32) / 8) {
       const uint32_t v = (g4::pack2<T>(__ldg(a.code + (e >> 4)), 0.f) & 0xFFFFu) | (g4::pack2<T>(__ldg(a.code + (e & 15)), 0.f) << 16);
-      *reinterpret_cast<uint4 *>(smem + e * 256 + j8 * 16) = make_uint4(v, v, v, v);
+      *reinterpret_cast<uint4 *>(lut + e * 256 + j8 * 16) = make_uint4(v, v, v, v);
     }
   }
   tc::fence_before_sync();
@@ -163,7 +176,7 @@ __global__ void __launch_bounds__(threads_for(NB16 * 16), 1) k_gemm4_small(const
     split = u - tile * a.splits;
     k_begin = split * a.kper;
     const int k_end = min(a.K, k_begin + a.kper);
-    nk = (k_end - k_begin) / TK;
+    nk = (k_end - k_begin) / (TK * KB);   // rounds
   };
 
   if (warp == 0) {
@@ -182,8 +195,8 @@ __global__ void __launch_bounds__(threads_for(NB16 * 16), 1) k_gemm4_small(const
           G4S_WAIT(t_w0, tc::smem_u32(emptyW + wslot), wphase ^ 1);
           if (tc::elect_one()) {
             const uint32_t fw = tc::smem_u32(fullW + wslot);
-            tc::mbar_arrive_expect_tx(fw, kStageW);
-            tc::tma_load_2d(tc::smem_u32(wring + wslot * kStageW), &tmW, fw, (k_begin + i * TK) >> 1, tile * TM);
+            tc::mbar_arrive_expect_tx(fw, kSlotW);
+            tc::tma_load_2d(tc::smem_u32(wring + wslot * kSlotW), &tmW, fw, (k_begin + i * TK * KB) >> 1, tile * TM);
           }
           __syncwarp();
           if (++wslot == kWSlots) { wslot = 0; wphase ^= 1; }
@@ -204,7 +217,9 @@ __global__ void __launch_bounds__(threads_for(NB16 * 16), 1) k_gemm4_small(const
           if (tc::elect_one()) {
             const uint32_t fb = tc::smem_u32(full + stage);
             tc::mbar_arrive_expect_tx(fb, (uint32_t)stageB);
-            tc::tma_load_2d(tc::smem_u32(ring + stage * stageB), &tmX, fb, k_begin + kb * TK, 0);
+#pragma unroll
+            for (int blk = 0; blk < KB; blk++)
+              tc::tma_load_2d(tc::smem_u32(ring + stage * stageB + blk * tileB), &tmX, fb, k_begin + (kb * KB + blk) * TK, 0);
           }
           __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
@@ -232,13 +247,16 @@ __global__ void __launch_bounds__(threads_for(NB16 * 16), 1) k_gemm4_small(const
           }
           G4S_WAIT(t_w0, tc::smem_u32(full + stage), phase);
           tc::fence_after_sync();
-          const uint64_t bdesc = tc::umma_desc_sw128_kmajor(tc::smem_u32(ring + stage * stageB));
-          const uint32_t ta = tmem_base + kAccCols + (uint32_t)(stage * 32);   // weights: 8 columns per k16 step
+          const uint32_t ta = tmem_base + kAccCols + (uint32_t)(stage * 32 * KB);   // weights: 8 columns per k16 step
           if (tc::elect_one()) {                               // the same lane every time (commit tracks the issuing thread)
             if (!G4S_DBG(2))
 #pragma unroll
-            for (int k = 0; k < TK / 16; k++)
-              umma_f16_ts(tmem_base + (uint32_t)(stage * NB), ta + 8 * k, bdesc + 2 * k, idesc, k != 0);
+            for (int blk = 0; blk < KB; blk++) {               // one accumulator slot per quantisation block
+              const uint64_t bdesc = tc::umma_desc_sw128_kmajor(tc::smem_u32(ring + stage * stageB + blk * tileB));
+#pragma unroll
+              for (int k = 0; k < TK / 16; k++)
+                umma_f16_ts(tmem_base + (uint32_t)((stage * KB + blk) * NB), ta + 32 * blk + 8 * k, bdesc + 2 * k, idesc, k != 0);
+            }
             tc::umma_commit(tc::smem_u32(done + stage));
           }
           __syncwarp();
@@ -252,8 +270,8 @@ __global__ void __launch_bounds__(threads_for(NB16 * 16), 1) k_gemm4_small(const
     const int dt = threadIdx.x - kFirstDq * 32;
     const int r = dt & 127;                               // weight row inside the tile
     const int grp = dt >> 7;
-    const uint32_t lane4 = (uint32_t)(lane * 4);
-    const uint32_t wring_s = tc::smem_u32(wring), smem_s = tc::smem_u32(smem);
+    const uint32_t lutlane = lut_s | (uint32_t)(lane * 4);   // PRMT operand b: bytes 0, 2, 3 of every lookup address
+    const uint32_t wring_s = tc::smem_u32(wring);
     // TMEM lanes of this warp (a warp reaches lanes 32 * (warp % 4) ..., and row r = 32 * (warp % 4) + lane)
     const uint32_t ta_warp = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kAccCols;
     int stage = grp % S, wslot = grp % kWSlots;
@@ -267,9 +285,13 @@ __global__ void __launch_bounds__(threads_for(NB16 * 16), 1) k_gemm4_small(const
     G4S_T0();
     for (int it = grp; it < total; it += G) {
       G4S_WAIT(t_w0, tc::smem_u32(fullW + wslot), wphase);
-      const uint32_t wp = wring_s + wslot * kStageW + r * 32;
-      const uint4 w0 = g4::lds128(wp), w1 = g4::lds128(wp + 16);
-      const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const uint32_t wp = wring_s + wslot * kSlotW + r * (32 * KB);
+      uint32_t w[8 * KB];
+#pragma unroll
+      for (int h = 0; h < 2 * KB; h++) {
+        const uint4 t = g4::lds128(wp + 16 * h);
+        w[4 * h] = t.x; w[4 * h + 1] = t.y; w[4 * h + 2] = t.z; w[4 * h + 3] = t.w;
+      }
       // The slot is handed back AFTER the stage has been written (below), not here: every table lookup consumes the
       // loaded registers, so by then both loads have returned.  An arrive issued right behind the LDS.128 (what this code
       // did first; an empty inline asm naming the registers does not make ptxas wait on the load scoreboard) let the
@@ -284,14 +306,17 @@ __global__ void __launch_bounds__(threads_for(NB16 * 16), 1) k_gemm4_small(const
 #ifdef G4S_TRACE
       const long long t_d0 = clock64();
 #endif
-      uint32_t o[32];                                     // word m = elements 2m (low half), 2m + 1 of this row's 64
-      if (!G4S_DBG(1))
 #pragma unroll
-      for (int c = 0; c < 8; c++)                         // one packed word = 8 elements
+      for (int blk = 0; blk < KB; blk++) {
+        uint32_t o[32];                                   // word m = elements 2m (low half), 2m + 1 of this row's 64
+        if (!G4S_DBG(1))
 #pragma unroll
-        for (int i = 0; i < 4; i++)                       // byte i of the word: even element in the high nibble = low half of the pair
-          o[c * 4 + i] = lds32(smem_s + __byte_perm(w[c], lane4, 0x7604u | (i << 4)));
-      tmem_st_32x32b_x32(ta_warp + (uint32_t)(stage * 32), o);
+        for (int c = 0; c < 8; c++)                       // one packed word = 8 elements
+#pragma unroll
+          for (int i = 0; i < 4; i++)                     // byte i of the word: even element in the high nibble = low half of the pair
+            o[c * 4 + i] = lds32(__byte_perm(w[blk * 8 + c], lutlane, 0x7604u | (i << 4)));
+        tmem_st_32x32b_x32(ta_warp + (uint32_t)(stage * 32 * KB + blk * 32), o);
+      }
       tmem_st_wait();
 #ifdef G4S_TRACE
       t_w2 += clock64() - t_d0;
@@ -326,24 +351,31 @@ __global__ void __launch_bounds__(threads_for(NB16 * 16), 1) k_gemm4_small(const
       float tot[HC];
 #pragma unroll
       for (int j = 0; j < HC; j++) tot[j] = 0.f;
-      // absmax of (row, block), two stages ahead
-      float am0 = __ldg(a.absmax + (ebase >> a.bs_shift));
-      float am1 = 1 < nk ? __ldg(a.absmax + ((ebase + (size_t)TK) >> a.bs_shift)) : 0.f;
+      // absmax of (row, block), one round ahead
+      float am_next[KB];
+#pragma unroll
+      for (int blk = 0; blk < KB; blk++) am_next[blk] = __ldg(a.absmax + ((ebase + (size_t)blk * TK) >> a.bs_shift));
       for (int kb = 0; kb < nk; kb++) {
-        const float am = am0;
-        am0 = am1;
-        if (kb + 2 < nk && !G4S_DBG(8)) am1 = __ldg(a.absmax + ((ebase + (size_t)(kb + 2) * TK) >> a.bs_shift));
+        float am[KB];
+#pragma unroll
+        for (int blk = 0; blk < KB; blk++) am[blk] = am_next[blk];
+        if (kb + 1 < nk && !G4S_DBG(8)) {
+#pragma unroll
+          for (int blk = 0; blk < KB; blk++) am_next[blk] = __ldg(a.absmax + ((ebase + (size_t)((kb + 1) * KB + blk) * TK) >> a.bs_shift));
+        }
         G4S_WAIT(t_w0, tc::smem_u32(done + stage), phase);
         tc::fence_after_sync();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * NB + col0);
-        // lift this warp's columns, hand the slot back, then scale
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * KB * NB + col0);
+        // lift this warp's columns of the round's KB slots, hand them back, then scale
 #ifdef G4S_TRACE
         const long long t_s0 = clock64();
 #endif
-        uint32_t v[HC / 8][8];
+        uint32_t v[KB][HC / 8][8];
         if (!G4S_DBG(4))
 #pragma unroll
-        for (int c = 0; c < HC / 8; c++) tmem_ld_32x32b_x8(taddr + c * 8, v[c]);
+        for (int blk = 0; blk < KB; blk++)
+#pragma unroll
+          for (int c = 0; c < HC / 8; c++) tmem_ld_32x32b_x8(taddr + blk * NB + c * 8, v[blk][c]);
         tc::tmem_ld_wait();
 #ifdef G4S_TRACE
         const long long t_s1 = clock64();
@@ -351,11 +383,13 @@ __global__ void __launch_bounds__(threads_for(NB16 * 16), 1) k_gemm4_small(const
 #endif
         tc::fence_before_sync();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(tc::smem_u32(full + stage));   // the slot may be overwritten by this stage's next round
+        if (lane == 0) tc::mbar_arrive(tc::smem_u32(full + stage));   // the slots may be overwritten by this stage's next round
 #pragma unroll
-        for (int c = 0; c < HC / 8; c++)
+        for (int blk = 0; blk < KB; blk++)
 #pragma unroll
-          for (int j = 0; j < 8; j++) tot[c * 8 + j] = __fmaf_rn(__uint_as_float(v[c][j]), am, tot[c * 8 + j]);
+          for (int c = 0; c < HC / 8; c++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) tot[c * 8 + j] = __fmaf_rn(__uint_as_float(v[blk][c][j]), am[blk], tot[c * 8 + j]);
 #ifdef G4S_TRACE
         asm volatile("" ::"f"(tot[0]), "f"(tot[HC - 1]));
         t_w2 += clock64() - t_s1;
@@ -383,9 +417,6 @@ __global__ void __launch_bounds__(threads_for(NB16 * 16), 1) k_gemm4_small(const
   if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
-constexpr size_t smem_bytes(int NB) {
-  return (size_t)kLut + (size_t)stages_for(NB) * (NB * 128) + (size_t)kWSlots * kStageW + 1024 /*align*/ + 512 /*barriers*/;
-}
 }  // namespace g4s
 
 // host: batch 9..64.  returns 0 ok, 1 not taken, 2 error
@@ -403,18 +434,22 @@ static int gemm_4bit_small(int batch, int N, int K, const T *A, const unsigned c
 #endif
   // K splits: the makespan of `units` equal units on `sms` persistent CTAs, each unit = its stages + ~6 stages of fill /
   // drain / epilogue; at least 8 stages per unit
-  const int kblocks = K / TK;
+  // one quantisation block per barrier round; two (NB <= 32, K allowing: TMEM holds S x KB x (NB + 32) columns) on request
+  static int kb_env = -1;   // BNB_B200_GEMM4_SMALL_KB=2: two blocks per round (measured slower: profiles/r2_gemm4_small_roles.md)
+  if (kb_env < 0) { const char *e = getenv("BNB_B200_GEMM4_SMALL_KB"); kb_env = (e && e[0] == '2') ? 2 : 1; }
+  const int KB = (a.NB <= 32 && (K / TK) % 2 == 0 && kb_env == 2) ? 2 : 1;
+  const int kblocks = K / (TK * KB);   // rounds
   int best = 1;
   long best_cost = -1;
-  for (int s = 1; s <= 16 && kblocks / s >= 8; s++) {
+  for (int s = 1; s <= 16 && kblocks / s >= 8 / KB; s++) {
     const int kb_per = (kblocks + s - 1) / s;
     const int ns = (kblocks + kb_per - 1) / kb_per;
     const long waves = ((long)a.tiles * ns + sms - 1) / sms;
-    const long cost = waves * (kb_per + 6);
+    const long cost = waves * (kb_per + 6 / KB);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
   }
   const int kb_per = (kblocks + best - 1) / best;
-  a.kper = kb_per * TK;
+  a.kper = kb_per * TK * KB;
   a.splits = (kblocks + kb_per - 1) / kb_per;
   bool ws_from_pool = false;
   if (a.splits > 1) {
@@ -423,24 +458,24 @@ static int gemm_4bit_small(int batch, int N, int K, const T *A, const unsigned c
   }
   CUtensorMap tmX, tmW;
   if (!make_tmap_2d(&tmX, A, 2, (uint64_t)batch, (uint64_t)K, (uint32_t)a.NB, TK, true, std::is_same<T, __nv_bfloat16>::value) ||
-      !make_tmap_2d(&tmW, B, 1, (uint64_t)N, (uint64_t)(K / 2), TM, TK / 2, false, false, false)) {
+      !make_tmap_2d(&tmW, B, 1, (uint64_t)N, (uint64_t)(K / 2), TM, (uint32_t)(TK / 2 * KB), false, false, false)) {
     if (ws_from_pool) cudaFreeAsync(a.ws, st);
     return 2;
   }
   const int units = a.tiles * a.splits;
   const int grid = units < sms ? units : sms;
-  const size_t smem = smem_bytes(a.NB);
-#define G4S_LAUNCH(NB16_)                                                                                                 \
+  const size_t smem = kSmemBytes;
+#define G4S_LAUNCH(NB16_, KB_)                                                                                            \
   do {                                                                                                                  \
-    auto kfn = k_gemm4_small<T, NB16_>;                                                                                 \
-    ensure_max_dynamic_smem(reinterpret_cast<const void *>(kfn), (int)smem_bytes(NB16_ * 16), "gemm_4bit small smem attr"); \
-    kfn<<<grid, threads_for(NB16_ * 16), smem, st>>>(tmX, tmW, a);                                                                     \
+    auto kfn = k_gemm4_small<T, NB16_, KB_>;                                                                            \
+    ensure_max_dynamic_smem(reinterpret_cast<const void *>(kfn), kSmemBytes, "gemm_4bit small smem attr");               \
+    kfn<<<grid, threads_for(NB16_ * 16), smem, st>>>(tmX, tmW, a);                                                     \
   } while (0)
   switch (a.NB / 16) {
-    case 1: G4S_LAUNCH(1); break;
-    case 2: G4S_LAUNCH(2); break;
-    case 3: G4S_LAUNCH(3); break;
-    default: G4S_LAUNCH(4); break;
+    case 1: if (KB == 2) G4S_LAUNCH(1, 2); else G4S_LAUNCH(1, 1); break;
+    case 2: if (KB == 2) G4S_LAUNCH(2, 2); else G4S_LAUNCH(2, 1); break;
+    case 3: G4S_LAUNCH(3, 1); break;
+    default: G4S_LAUNCH(4, 1); break;
   }
 #undef G4S_LAUNCH
   check_launch("gemm_4bit (small batch, tcgen05)");

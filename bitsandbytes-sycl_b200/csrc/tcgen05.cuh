@@ -36,12 +36,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
                : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   return done != 0;
 }
-// bounded spin: a protocol bug must trap (sticky error the host sees), never hang the GPU
+// try_wait with a suspend-time hint (ns): the thread may sleep inside the instruction instead of coming back to spin
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t done;
+  asm volatile("{\n .reg .pred P;\n mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n selp.u32 %0, 1, 0, P;\n}"
+               : "=r"(done) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+  return done != 0;
+}
+// bounded spin: a protocol bug must trap (sticky error the host sees), never hang the GPU.  Waiting warps share issue
+// slots with working ones, so the loop is as thin as it can be: one try_wait (suspend hint) and a counter; the clock is
+// read once per 1024 rounds.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) { printf("bnb_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  long long t0 = 0;
+  for (uint32_t spins = 1;; spins++) {
+    if (mbar_try_wait_hint(bar, parity, 20000u)) return;
+    if ((spins & 1023u) == 0) {
+      const long long t = clock64();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000ll) { printf("bnb_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
   }
 }
 
