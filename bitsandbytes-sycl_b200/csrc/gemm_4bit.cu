@@ -298,6 +298,7 @@ static float *workspace(int dev, size_t bytes, cudaStream_t st, bool *from_pool)
 static int ilog2_(int v) { int s = 0; while ((1 << s) < v) s++; return s; }
 
 #include "gemm_4bit_small.cuh"
+#include "gemm_4bit_wide.cuh"
 
 // returns 0 ok, 1 shape not taken by the fused kernel (caller uses dequantize + matmul), 2 error
 template <typename T>
@@ -321,6 +322,11 @@ int gemm_4bit(int batch, int N, int K, const T *A, const unsigned char *B, const
   if (small_off < 0) { const char *e = getenv("BNB_B200_GEMM4_SMALL"); small_off = (e && e[0] == '0') ? 1 : 0; }
   if (batch <= 64 && !small_off && K / TK >= 8)
     return gemm_4bit_small<T>(batch, N, K, A, B, absmax, datatype, bias, out, ilog2_(blocksize), num_sms[dev], dev, st);
+
+  static int wide_off = -1;
+  if (wide_off < 0) { const char *e = getenv("BNB_B200_GEMM4_WIDE"); wide_off = (e && e[0] == '0') ? 1 : 0; }
+  if (!wide_off && K / TK >= 4)
+    return gemm_4bit_wide<T>(batch, N, K, A, B, absmax, datatype, bias, out, ilog2_(blocksize), num_sms[dev], dev, st);
 
   Args a{};
   a.batch = batch; a.N = N; a.K = K; a.blocksize = blocksize; a.bs_shift = ilog2_(blocksize);
