@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(threads_for(NB16 * 16), 1) k_gemm4_small(const
 
 }  // namespace g4s
 
-// host: batch 9..64.  returns 0 ok, 1 not taken, 2 error
+// host: batch <= 32.  returns 0 ok, 2 error
 template <typename T>
 static int gemm_4bit_small(int batch, int N, int K, const T *A, const unsigned char *B, const float *absmax, const float *datatype,
                            const T *bias, T *out, int bs_shift, int sms, int dev, cudaStream_t st) {
@@ -471,12 +471,8 @@ static int gemm_4bit_small(int batch, int N, int K, const T *A, const unsigned c
     ensure_max_dynamic_smem(reinterpret_cast<const void *>(kfn), kSmemBytes, "gemm_4bit small smem attr");               \
     kfn<<<grid, threads_for(NB16_ * 16), smem, st>>>(tmX, tmW, a);                                                     \
   } while (0)
-  switch (a.NB / 16) {
-    case 1: if (KB == 2) G4S_LAUNCH(1, 2); else G4S_LAUNCH(1, 1); break;
-    case 2: if (KB == 2) G4S_LAUNCH(2, 2); else G4S_LAUNCH(2, 1); break;
-    case 3: G4S_LAUNCH(3, 1); break;
-    default: G4S_LAUNCH(4, 1); break;
-  }
+  if (a.NB == 16) { if (KB == 2) G4S_LAUNCH(1, 2); else G4S_LAUNCH(1, 1); }
+  else { if (KB == 2) G4S_LAUNCH(2, 2); else G4S_LAUNCH(2, 1); }
 #undef G4S_LAUNCH
   check_launch("gemm_4bit (small batch, tcgen05)");
   if (a.splits > 1) {

@@ -21,11 +21,9 @@ namespace g4w {
 constexpr int TM = 128, TK = 64;
 constexpr int kStageW = TM * 32;           // 4 KB of packed weights per stage
 constexpr int kWSlots = 12;
-constexpr int kDqGroups = 3;
-static_assert(kWSlots % kDqGroups == 0, "a packed-weight slot must belong to one dequant group");
-constexpr int kDqWarps = 4 * kDqGroups;
+static_assert(kWSlots % 3 == 0 && kWSlots % 4 == 0, "a packed-weight slot must belong to one dequant group");
 constexpr int kFirstDq = 4;
-constexpr int kThreads = (kFirstDq + kDqWarps) * 32;
+__host__ __device__ constexpr int threads_for(int G) { return (kFirstDq + 4 * G) * 32; }
 constexpr int kLut = 65536;
 // shared window: [base .. +48 KB) packed ring | barriers | table at the first 64 KB boundary | activation ring behind it
 constexpr uint32_t kXRingMax = 96 * 1024;
@@ -51,10 +49,11 @@ __device__ __forceinline__ float2 lds64f(uint32_t saddr) {
   return v;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads, 1) k_gemm4_wide(const __grid_constant__ CUtensorMap tmX,
+template <typename T, int G>   // G dequant groups of four warps (<= stages)
+__global__ void __launch_bounds__(threads_for(G), 1) k_gemm4_wide(const __grid_constant__ CUtensorMap tmX,
                                                           const __grid_constant__ CUtensorMap tmW, const Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int kDqWarps = 4 * G;
   const int NB = a.NB;
   const int S = stages_for(NB);
   const int stageB = NB * 128;               // activation tile: NB rows x 64 T, SWIZZLE_128B
@@ -155,7 +154,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm4_wide(const __grid_constan
     }
   } else if (warp >= kFirstDq) {
     // ================= dequant producers: packed bytes -> T(code * absmax) pairs -> TMEM =================
-    constexpr int G = kDqGroups;
     const int dt = threadIdx.x - kFirstDq * 32;
     const int r = dt & 127;                               // weight row inside the tile
     const int grp = dt >> 7;
@@ -260,8 +258,15 @@ static int gemm_4bit_wide(int batch, int N, int K, const T *A, const unsigned ch
     if (ws_from_pool) cudaFreeAsync(a.ws, st);
     return 2;
   }
-  ensure_max_dynamic_smem(reinterpret_cast<const void *>(k_gemm4_wide<T>), kSmemBytes, "gemm_4bit wide smem attr");
-  k_gemm4_wide<T><<<dim3(tiles, a.splits), kThreads, kSmemBytes, st>>>(tmX, tmW, a);
+  static int g_env = -1;   // BNB_B200_GEMM4_WIDE_G=3: three dequant groups at every width (A/B measurements)
+  if (g_env < 0) { const char *e = getenv("BNB_B200_GEMM4_WIDE_G"); g_env = (e && e[0] == '3') ? 3 : 4; }
+  if (stages_for(a.NB) >= 4 && g_env == 4) {
+    ensure_max_dynamic_smem(reinterpret_cast<const void *>(k_gemm4_wide<T, 4>), kSmemBytes, "gemm_4bit wide smem attr");
+    k_gemm4_wide<T, 4><<<dim3(tiles, a.splits), threads_for(4), kSmemBytes, st>>>(tmX, tmW, a);
+  } else {
+    ensure_max_dynamic_smem(reinterpret_cast<const void *>(k_gemm4_wide<T, 3>), kSmemBytes, "gemm_4bit wide smem attr");
+    k_gemm4_wide<T, 3><<<dim3(tiles, a.splits), threads_for(3), kSmemBytes, st>>>(tmX, tmW, a);
+  }
   check_launch("gemm_4bit (wide, tcgen05)");
   if (a.splits > 1) {
     const size_t total = (size_t)batch * N;
