@@ -51,6 +51,15 @@ CASES = [
     (256, 14336, 4096, "fp16", True, 64, False),
     (128, 4096, 14336, "fp16", True, 64, False),
     (20, 14336, 4096, "bf16", True, 64, False),    # batch between the GEMV route (<= 8) and a full 32-row tile
+    # routing edges of round 2's two kernels
+    (48, 512, 4096, "bf16", True, 64, True),       # first width of the wide kernel (NB = 48, four dequant groups)
+    (64, 14336, 4096, "bf16", True, 64, False),
+    (192, 256, 4096, "bf16", True, 64, False),     # last width with a four-stage activation ring
+    (200, 256, 2048, "fp16", False, 64, True),     # NB = 208: three stages, three groups
+    (16, 256, 256, "bf16", True, 64, False),       # K too short for the small kernel (4 blocks): wide kernel at batch 16
+    (24, 300, 320, "fp16", False, 64, True),       # 5 blocks, ragged N
+    (100, 200, 1024, "fp16", True, 256, False),    # blocksize 256 in the wide kernel
+    (32, 384, 1024, "fp16", False, 128, True),     # blocksize 128 in the small kernel, NB = 32
 ]
 
 
