@@ -155,7 +155,10 @@ __global__ void __launch_bounds__(threads_for(NB16 * 16), 1) k_gemm4_small(const
       tc::fence_barrier_init();
     }
     __syncwarp();
+    asm volatile("bar.sync 1, 96;" ::: "memory");        // the two TMA warps need only the mbarriers: they start now
     tc::tmem_alloc(tc::smem_u32(tmem_slot), 512);
+  } else if (warp == 0 || warp == 2) {
+    asm volatile("bar.sync 1, 96;" ::: "memory");
   }
   if (warp >= kFirstDq && warp < kFirstSc) {
     // byte-pair table e -> {T(code[e >> 4]), T(code[e & 15])}, replicated for the 32 lanes: 8 threads per entry
@@ -166,10 +169,15 @@ __global__ void __launch_bounds__(threads_for(NB16 * 16), 1) k_gemm4_small(const
       *reinterpret_cast<uint4 *>(lut + e * 256 + j8 * 16) = make_uint4(v, v, v, v);
     }
   }
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  // everybody else also needs the table and the TMEM allocation: barrier 2 joins all warps but the two producers, whose
+  // first loads are in flight while the table is being written
+  uint32_t tmem_base = 0;
+  if (warp != 0 && warp != 2) {
+    tc::fence_before_sync();
+    asm volatile("bar.sync 2, %0;" ::"r"((int)blockDim.x - 64) : "memory");
+    tc::fence_after_sync();
+    tmem_base = *tmem_slot;
+  }
 
   auto unit_range = [&](int u, int &tile, int &split, int &k_begin, int &nk) {
     tile = u / a.splits;

@@ -91,7 +91,10 @@ __global__ void __launch_bounds__(threads_for(G), 1) k_gemm4_wide(const __grid_c
       tc::fence_barrier_init();
     }
     __syncwarp();
+    asm volatile("bar.sync 1, 96;" ::: "memory");        // the two TMA warps need only the mbarriers: they start now
     tc::tmem_alloc(tc::smem_u32(tmem_slot), 512);
+  } else if (warp == 0 || warp == 2) {
+    asm volatile("bar.sync 1, 96;" ::: "memory");
   }
   if (warp >= kFirstDq) {
     // table e -> {code[e >> 4], code[e & 15]} (fp32 pair; the even element sits in the high nibble), one pair per lane
@@ -102,10 +105,15 @@ __global__ void __launch_bounds__(threads_for(G), 1) k_gemm4_wide(const __grid_c
       *reinterpret_cast<float4 *>(lut + e * 256 + (idx & 15) * 16) = make_float4(c0, c1, c0, c1);
     }
   }
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  // everybody else also needs the table and the TMEM allocation: barrier 2 joins all warps but the two producers, whose
+  // first loads are in flight while the table is being written
+  uint32_t tmem_base = 0;
+  if (warp != 0 && warp != 2) {
+    tc::fence_before_sync();
+    asm volatile("bar.sync 2, %0;" ::"r"((int)blockDim.x - 64) : "memory");
+    tc::fence_after_sync();
+    tmem_base = *tmem_slot;
+  }
 
   if (warp == 0) {
     // ================= packed weights: TMA into the deep ring =================
