@@ -68,12 +68,19 @@ bool make_tmap_2d(CUtensorMap *map, const void *base, int elem_bytes, uint64_t r
 // tcgen05 kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int BM = 128, BN = 256, BK = 128;  // BK in bytes == int8 elements
-constexpr int kStages = 4;
-constexpr int kStageA = BM * BK, kStageB = BN * BK, kStageBytes = kStageA + kStageB;  // 16 KB + 32 KB
+// CG = CTAs per MMA (tcgen05 cta_group).  CG = 2: a CTA pair (cluster of two, one TPC) computes a 256 x 256 tile; each CTA
+// loads ITS 128 rows of A and ITS 128 of the 256 rows of B (32 KB per stage instead of 48), the leader issues
+// tcgen05.mma.cta_group::2 with M = 256 and each CTA's TMEM receives its own 128 x 256 half of the result.  Per stage and
+// SM the operand traffic through shared memory drops from 96 KB (768 cycles at 128 B/cycle, more than the 528 cycles the
+// four MMAs take) to 64 KB.
+constexpr int kStageA = BM * BK;   // 16 KB
+__host__ __device__ constexpr int stage_b_bytes(int CG) { return (BN / CG) * BK; }          // 32 KB / 16 KB
+__host__ __device__ constexpr int stage_bytes(int CG) { return kStageA + stage_b_bytes(CG); }
+__host__ __device__ constexpr int stages_for(int CG) { return CG == 2 ? 6 : 4; }           // 192 KB of operand ring either way
 constexpr int kEpiThreads = 256;                 // 8 epilogue warps: two per TMEM lane quarter, each takes half the columns
 constexpr int kIgemmThreads = 64 + kEpiThreads;
 constexpr int kTmemCols = 512;
-constexpr int kIgemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * (4 + 4) /*col stats + bias (fp32)*/ +
+constexpr int kIgemmSmem = 4 * (kStageA + BN * BK) + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * (4 + 4) /*col stats + bias (fp32)*/ +
                            2 * BN * 8 * 4 /*outlier columns of the weight as fp32, per accumulator buffer*/;
 
 enum { EPI_INT32 = 0, EPI_DEQUANT_FP16 = 1, EPI_INT32_COL32 = 2, EPI_S8_COL32 = 3 };   // the last two: the reference ABI's C layout, written by the epilogue
@@ -93,9 +100,44 @@ struct IgemmArgs {
   const int *nout;         // device-side number of outlier columns
 };
 
-template <int EPI>
+namespace cg2 {
+__device__ __forceinline__ uint32_t cta_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address with the peer bit cleared = the even (leader) CTA of the pair
+// both CTAs of the pair load their own box; the bytes are counted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap *m, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the mbarrier at the same offset in BOTH CTAs once every MMA issued so far has completed
+__device__ __forceinline__ void umma_commit_both(uint32_t bar) {
+  asm volatile("{\n .reg .b16 m;\n mov.b16 m, 3;\n tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n}"
+               ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrive on the mbarrier at local address `bar` of CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile("{\n .reg .b32 r;\n mapa.shared::cluster.u32 r, %0, %1;\n mbarrier.arrive.release.cluster.shared::cluster.b64 _, [r];\n}"
+               ::"r"(bar), "r"(rank) : "memory");
+}
+}  // namespace cg2
+
+template <int EPI, int CG>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 k_igemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmArgs a) {
+  constexpr int kStages = stages_for(CG), kStageBytes = stage_bytes(CG);
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
@@ -106,47 +148,57 @@ k_igemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   float4 *s_sb = reinterpret_cast<float4 *>(s_bias + 2 * BN);                   // [2][BN][8 floats] = 2 float4 per column
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_m = (a.M + BM - 1) / BM, num_n = (a.N + BN - 1) / BN;
+  const int rank = CG == 2 ? (int)cg2::cta_rank() : 0;          // 0 = leader of the pair (issues the MMAs)
+  const int unit = (int)blockIdx.x / CG, units = (int)gridDim.x / CG;   // a unit = a CTA or a CTA pair
+  const int num_m = (a.M + BM * CG - 1) / (BM * CG), num_n = (a.N + BN - 1) / BN;
   const int tiles = num_m * num_n, kblocks = (a.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmA); tc::prefetch_tmap(&tmB); }
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < kStages; s++) { tc::mbar_init(tc::smem_u32(full + s), 1); tc::mbar_init(tc::smem_u32(empty + s), 1); }
-      for (int i = 0; i < 2; i++) { tc::mbar_init(tc::smem_u32(tfull + i), 1); tc::mbar_init(tc::smem_u32(tempty + i), kEpiThreads / 32); }
+      // the accumulator is free again when the epilogue warps of BOTH CTAs have read their half (they arrive on the leader's barrier)
+      for (int i = 0; i < 2; i++) { tc::mbar_init(tc::smem_u32(tfull + i), 1); tc::mbar_init(tc::smem_u32(tempty + i), CG * kEpiThreads / 32); }
       tc::fence_barrier_init();
     }
     __syncwarp();
-    tc::tmem_alloc(tc::smem_u32(tmem_slot), kTmemCols);
+    if (CG == 2) cg2::tmem_alloc(tc::smem_u32(tmem_slot), kTmemCols); else tc::tmem_alloc(tc::smem_u32(tmem_slot), kTmemCols);
   }
   tc::fence_before_sync();
-  __syncthreads();
+  if (CG == 2) cg2::cluster_sync(); else __syncthreads();   // the peer's mbarriers must exist before anything signals them
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int m_blk = tile % num_m, n_blk = tile / num_m;
-        for (int kb = 0; kb < kblocks; kb++) {
-          tc::mbar_wait(tc::smem_u32(empty + stage), phase ^ 1);
+    // ================= TMA producer (whole warp runs the loop, one elected lane issues) =================
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = unit; tile < tiles; tile += units) {
+      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      for (int kb = 0; kb < kblocks; kb++) {
+        tc::mbar_wait(tc::smem_u32(empty + stage), phase ^ 1);
+        if (tc::elect_one()) {
           const uint32_t fb = tc::smem_u32(full + stage);
-          tc::mbar_arrive_expect_tx(fb, kStageBytes);
-          uint8_t *sa = smem + stage * kStageBytes;
-          tc::tma_load_2d(tc::smem_u32(sa), &tmA, fb, kb * BK, m_blk * BM);
-          tc::tma_load_2d(tc::smem_u32(sa + kStageA), &tmB, fb, kb * BK, n_blk * BN);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          const uint32_t sa = tc::smem_u32(smem + stage * kStageBytes);
+          if (CG == 2) {
+            if (rank == 0) tc::mbar_arrive_expect_tx(fb, 2 * kStageBytes);   // the bytes of both CTAs land on the leader's barrier
+            cg2::tma_load_2d(sa, &tmA, fb, kb * BK, (m_blk * 2 + rank) * BM);
+            cg2::tma_load_2d(sa + kStageA, &tmB, fb, kb * BK, n_blk * BN + rank * (BN / 2));
+          } else {
+            tc::mbar_arrive_expect_tx(fb, kStageBytes);
+            tc::tma_load_2d(sa, &tmA, fb, kb * BK, m_blk * BM);
+            tc::tma_load_2d(sa + kStageA, &tmB, fb, kb * BK, n_blk * BN);
+          }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::umma_idesc(tc::kCFormatS32, 1u, BM, BN);
+    // ================= MMA issuer (the leader CTA of a pair only) =================
+    if (rank == 0) {
+      constexpr uint32_t idesc = tc::umma_idesc(tc::kCFormatS32, 1u, BM * CG, BN);
       int stage = 0; uint32_t phase = 0; int it = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
+      for (int tile = unit; tile < tiles; tile += units, it++) {
         const int acc = it & 1; const uint32_t use = (uint32_t)(it >> 1);
         tc::mbar_wait(tc::smem_u32(tempty + acc), (use & 1) ^ 1);
         tc::fence_after_sync();
@@ -157,13 +209,20 @@ k_igemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t sa = tc::smem_u32(smem + stage * kStageBytes);
           const uint64_t adesc = tc::umma_desc_sw128_kmajor(sa);
           const uint64_t bdesc = tc::umma_desc_sw128_kmajor(sa + kStageA);
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 32; k++)
-            tc::umma_i8(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          tc::umma_commit(tc::smem_u32(empty + stage));
+            for (int k = 0; k < BK / 32; k++) {
+              if (CG == 2) cg2::umma_i8(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              else tc::umma_i8(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            }
+            if (CG == 2) cg2::umma_commit_both(tc::smem_u32(empty + stage)); else tc::umma_commit(tc::smem_u32(empty + stage));
+            if (kb == kblocks - 1) {
+              if (CG == 2) cg2::umma_commit_both(tc::smem_u32(tfull + acc)); else tc::umma_commit(tc::smem_u32(tfull + acc));
+            }
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        tc::umma_commit(tc::smem_u32(tfull + acc));
       }
     }
   } else {
@@ -172,10 +231,10 @@ k_igemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int half_n = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;  // 0..255
     int it = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
+    for (int tile = unit; tile < tiles; tile += units, it++) {
       const int m_blk = tile % num_m, n_blk = tile / num_m;
       const int acc = it & 1; const uint32_t use = (uint32_t)(it >> 1);
-      const int row = m_blk * BM + q * 32 + lane;
+      const int row = (m_blk * CG + rank) * BM + q * 32 + lane;
       float rs = 0.f;
       float arow[8];
       int nout = 0;
@@ -326,13 +385,15 @@ k_igemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tc::smem_u32(tempty + acc));
+      if (lane == 0) {
+        if (CG == 2) cg2::mbar_arrive_remote(tc::smem_u32(tempty + acc), 0); else tc::mbar_arrive(tc::smem_u32(tempty + acc));
+      }
     }
   }
 
   tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, kTmemCols);
+  if (CG == 2) cg2::cluster_sync(); else __syncthreads();    // nobody of the pair may still be reading TMEM or signalling a peer barrier
+  if (warp == 1) { if (CG == 2) cg2::tmem_dealloc(tmem_base, kTmemCols); else tc::tmem_dealloc(tmem_base, kTmemCols); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -405,18 +466,34 @@ static int igemm_rowmajor(const signed char *A, const signed char *B, const Igem
   if (tma_ok) {
     CUtensorMap tmA, tmB;
     if (!make_tmap_2d(&tmA, A, 1, (uint64_t)a.M, (uint64_t)a.K, BM, BK, false, false)) return 2;
-    if (!make_tmap_2d(&tmB, B, 1, (uint64_t)a.N, (uint64_t)a.K, BN, BK, false, false)) return 2;
     int sms = kNumSMs, dev = 0;
     cudaGetDevice(&dev);
-    static bool attr_set[64] = {false};          // the attribute is per device: one process may drive several GPUs
-    if (!attr_set[dev & 63]) {
-      ensure_max_dynamic_smem(reinterpret_cast<const void *>(k_igemm_tcgen05<EPI>), kIgemmSmem, "igemm smem attr");
-      attr_set[dev & 63] = true;
-    }
-    const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = tiles < sms ? tiles : sms;
-    k_igemm_tcgen05<EPI><<<grid, kIgemmThreads, kIgemmSmem, st>>>(tmA, tmB, a);
+    static int one_cta = -1;   // BNB_B200_IGEMM_CG=1: one CTA per MMA everywhere (A/B measurements)
+    if (one_cta < 0) { const char *e = getenv("BNB_B200_IGEMM_CG"); one_cta = (e && e[0] == '1') ? 1 : 0; }
+    const bool pair = !one_cta && a.M > BM && sms >= 2;
+    if (!make_tmap_2d(&tmB, B, 1, (uint64_t)a.N, (uint64_t)a.K, pair ? BN / 2 : BN, BK, false, false)) return 2;
+    if (pair) {
+      // CTA pairs: a cluster of two computes 256 x 256 tiles with tcgen05 cta_group::2
+      ensure_max_dynamic_smem(reinterpret_cast<const void *>(k_igemm_tcgen05<EPI, 2>), kIgemmSmem, "igemm smem attr");
+      const int tiles = ceil_div(a.M, 2 * BM) * ceil_div(a.N, BN);
+      const int pairs = tiles < sms / 2 ? tiles : sms / 2;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * pairs);
+      cfg.blockDim = dim3(kIgemmThreads);
+      cfg.dynamicSmemBytes = kIgemmSmem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      cudaLaunchKernelEx(&cfg, k_igemm_tcgen05<EPI, 2>, tmA, tmB, a);
+    } else {
+      ensure_max_dynamic_smem(reinterpret_cast<const void *>(k_igemm_tcgen05<EPI, 1>), kIgemmSmem, "igemm smem attr");
+      const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
+      const int grid = tiles < sms ? tiles : sms;
+      k_igemm_tcgen05<EPI, 1><<<grid, kIgemmThreads, kIgemmSmem, st>>>(tmA, tmB, a);
+    }
   } else {
     dim3 grid(ceil_div(a.N, 64), ceil_div(a.M, 64));
     k_igemm_simt<EPI><<<grid, 256, 0, st>>>(A, B, a);
