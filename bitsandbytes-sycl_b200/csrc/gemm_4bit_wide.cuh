@@ -28,7 +28,8 @@ constexpr int kLut = 65536;
 // shared window: [base .. +48 KB) packed ring | barriers | table at the first 64 KB boundary | activation ring behind it
 constexpr uint32_t kXRingMax = 96 * 1024;
 constexpr int kSmemBytes = 223 * 1024;     // base 0x400: table at 0x10000, activation ring 0x20000 .. 0x38000
-__host__ __device__ constexpr int stages_for(int NB) { return NB <= 192 ? 4 : 3; }   // S * NB * 128 <= 96 KB, S >= groups
+// activation ring: S * (NB / CG) * 128 <= 96 KB, S >= groups; a CTA pair (CG = 2) holds half of the batch rows per CTA
+__host__ __device__ constexpr int stages_for(int NB, int CG) { return (CG == 2 || NB <= 192) ? 4 : 3; }
 constexpr uint32_t kACol = 256;            // TMEM: accumulator in columns [0, NB), operand stages of 32 columns from 256
 
 struct Args {
@@ -49,14 +50,18 @@ __device__ __forceinline__ float2 lds64f(uint32_t saddr) {
   return v;
 }
 
-template <typename T, int G>   // G dequant groups of four warps (<= stages)
+// CG = 2: a CTA pair (cluster of two) computes 256 weight rows; each CTA dequantises ITS 128 rows into its own TMEM and
+// loads ITS half of the activation rows, the leader issues tcgen05.mma.cta_group::2 (M = 256).  Halves the activation
+// traffic through shared memory, the estimated bound of the one-CTA kernel at NB >= 128.
+template <typename T, int G, int CG>   // G dequant groups of four warps (<= stages)
 __global__ void __launch_bounds__(threads_for(G), 1) k_gemm4_wide(const __grid_constant__ CUtensorMap tmX,
                                                           const __grid_constant__ CUtensorMap tmW, const Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int kDqWarps = 4 * G;
   const int NB = a.NB;
-  const int S = stages_for(NB);
-  const int stageB = NB * 128;               // activation tile: NB rows x 64 T, SWIZZLE_128B
+  const int S = stages_for(NB, CG);
+  const int stageB = (NB / CG) * 128;        // this CTA's activation rows x 64 T, SWIZZLE_128B
+  const int rank = CG == 2 ? (int)cg2::cta_rank() : 0;
   const uint32_t smem_base = tc::smem_u32(smem_raw);
   const uint32_t wring_s = (smem_base + 1023u) & ~1023u;
   const uint32_t bars_s = wring_s + kWSlots * kStageW;
@@ -80,7 +85,7 @@ __global__ void __launch_bounds__(threads_for(G), 1) k_gemm4_wide(const __grid_c
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < S; s++) {
-        tc::mbar_init(tc::smem_u32(full + s), 4 + 1);   // dequant warps of the group + activation expect_tx
+        tc::mbar_init(tc::smem_u32(full + s), 4 * CG + 1);   // dequant warps of the group (of both CTAs) + activation expect_tx
         tc::mbar_init(tc::smem_u32(done + s), 1);       // tcgen05.commit: operands consumed
       }
       for (int s = 0; s < kWSlots; s++) {
@@ -91,9 +96,9 @@ __global__ void __launch_bounds__(threads_for(G), 1) k_gemm4_wide(const __grid_c
       tc::fence_barrier_init();
     }
     __syncwarp();
-    asm volatile("bar.sync 1, 96;" ::: "memory");        // the two TMA warps need only the mbarriers: they start now
-    tc::tmem_alloc(tc::smem_u32(tmem_slot), 512);
-  } else if (warp == 0 || warp == 2) {
+    if (CG == 1) asm volatile("bar.sync 1, 96;" ::: "memory");   // the two TMA warps need only the mbarriers: they start now
+    if (CG == 2) cg2::tmem_alloc(tc::smem_u32(tmem_slot), 512); else tc::tmem_alloc(tc::smem_u32(tmem_slot), 512);
+  } else if (CG == 1 && (warp == 0 || warp == 2)) {
     asm volatile("bar.sync 1, 96;" ::: "memory");
   }
   if (warp >= kFirstDq) {
@@ -108,7 +113,12 @@ __global__ void __launch_bounds__(threads_for(G), 1) k_gemm4_wide(const __grid_c
   // everybody else also needs the table and the TMEM allocation: barrier 2 joins all warps but the two producers, whose
   // first loads are in flight while the table is being written
   uint32_t tmem_base = 0;
-  if (warp != 0 && warp != 2) {
+  if (CG == 2) {           // the peer's mbarriers must exist before anything signals them: one cluster barrier for everybody
+    tc::fence_before_sync();
+    cg2::cluster_sync();
+    tc::fence_after_sync();
+    tmem_base = *tmem_slot;
+  } else if (warp != 0 && warp != 2) {
     tc::fence_before_sync();
     asm volatile("bar.sync 2, %0;" ::"r"((int)blockDim.x - 64) : "memory");
     tc::fence_after_sync();
@@ -135,27 +145,34 @@ __global__ void __launch_bounds__(threads_for(G), 1) k_gemm4_wide(const __grid_c
       tc::mbar_wait(tc::smem_u32(done + stage), phase ^ 1);
       if (tc::elect_one()) {
         const uint32_t fb = tc::smem_u32(full + stage);
-        tc::mbar_arrive_expect_tx(fb, (uint32_t)stageB);
-        tc::tma_load_2d(xring_s + stage * stageB, &tmX, fb, k_begin + kb * TK, 0);
+        if (CG == 2) {
+          if (rank == 0) tc::mbar_arrive_expect_tx(fb, (uint32_t)(2 * stageB));   // both halves are counted on the leader's barrier
+          cg2::tma_load_2d(xring_s + stage * stageB, &tmX, fb, k_begin + kb * TK, rank * (NB / 2));
+        } else {
+          tc::mbar_arrive_expect_tx(fb, (uint32_t)stageB);
+          tc::tma_load_2d(xring_s + stage * stageB, &tmX, fb, k_begin + kb * TK, 0);
+        }
       }
       __syncwarp();
       if (++stage == S) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     // ================= MMA issuer: four k16 steps per stage into the one accumulator =================
-    const uint32_t idesc = tc::umma_idesc(tc::kCFormatF32, std::is_same<T, __nv_bfloat16>::value ? 1u : 0u, TM, (uint32_t)NB);
+    const uint32_t idesc = tc::umma_idesc(tc::kCFormatF32, std::is_same<T, __nv_bfloat16>::value ? 1u : 0u, TM * CG, (uint32_t)NB);
     int stage = 0; uint32_t phase = 0;
-    for (int kb = 0; kb < nk; kb++) {
+    for (int kb = 0; kb < (rank == 0 ? nk : 0); kb++) {     // the leader of a pair issues for both
       tc::mbar_wait(tc::smem_u32(full + stage), phase);
       tc::fence_after_sync();
       const uint64_t bdesc = tc::umma_desc_sw128_kmajor(xring_s + stage * stageB);
       const uint32_t ta = tmem_base + kACol + (uint32_t)(stage * 32);
       if (tc::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < TK / 16; k++)
-          g4s::umma_f16_ts(tmem_base, ta + 8 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-        tc::umma_commit(tc::smem_u32(done + stage));
-        if (kb == nk - 1) tc::umma_commit(tc::smem_u32(tfull));
+        for (int k = 0; k < TK / 16; k++) {
+          if (CG == 2) cg2::umma_f16_ts(tmem_base, ta + 8 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          else g4s::umma_f16_ts(tmem_base, ta + 8 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        }
+        if (CG == 2) cg2::umma_commit_both(tc::smem_u32(done + stage)); else tc::umma_commit(tc::smem_u32(done + stage));
+        if (kb == nk - 1) { if (CG == 2) cg2::umma_commit_both(tc::smem_u32(tfull)); else tc::umma_commit(tc::smem_u32(tfull)); }
       }
       __syncwarp();
       if (++stage == S) { stage = 0; phase ^= 1; }
@@ -199,7 +216,7 @@ __global__ void __launch_bounds__(threads_for(G), 1) k_gemm4_wide(const __grid_c
       __syncwarp();
       if (lane == 0) {
         tc::mbar_arrive(wbar);
-        tc::mbar_arrive(tc::smem_u32(full + stage));
+        if (CG == 2) cg2::mbar_arrive_remote(tc::smem_u32(full + stage), 0); else tc::mbar_arrive(tc::smem_u32(full + stage));
       }
       stage += G;
       while (stage >= S) { stage -= S; phase ^= 1u; }
@@ -232,8 +249,8 @@ __global__ void __launch_bounds__(threads_for(G), 1) k_gemm4_wide(const __grid_c
   }
 
   tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+  if (CG == 2) cg2::cluster_sync(); else __syncthreads();
+  if (warp == 1) { if (CG == 2) cg2::tmem_dealloc(tmem_base, 512); else tc::tmem_dealloc(tmem_base, 512); }
 }
 }  // namespace g4w
 
@@ -244,10 +261,13 @@ static int gemm_4bit_wide(int batch, int N, int K, const T *A, const unsigned ch
   using namespace g4w;
   Args a{};
   a.batch = batch; a.N = N; a.K = K; a.bs_shift = bs_shift;
-  a.NB = (batch + 15) / 16 * 16;
-  a.B = B; a.absmax = absmax; a.code = datatype; a.bias = bias; a.out = out;
+  static int pair_min = -1;   // BNB_B200_GEMM4_WIDE_PAIR=<batch>: CTA pairs from this batch on (0: never)
+  if (pair_min < 0) { const char *e = getenv("BNB_B200_GEMM4_WIDE_PAIR"); pair_min = e ? atoi(e) : 160; }
   const int tiles = (N + TM - 1) / TM;
-  int splits = sms / tiles;                                // K is split until the grid fills the SMs
+  const bool pair = pair_min > 0 && batch >= pair_min && tiles >= 2;
+  a.NB = pair ? (batch + 31) / 32 * 32 : (batch + 15) / 16 * 16;
+  a.B = B; a.absmax = absmax; a.code = datatype; a.bias = bias; a.out = out;
+  int splits = sms / ((tiles + 1) / 2 * 2);                                // K is split until the grid fills the SMs
   const int kblocks = K / TK;
   if (splits > kblocks / 8) splits = kblocks / 8;          // at least 8 stages of work per CTA
   if (splits > 16) splits = 16;
@@ -261,19 +281,31 @@ static int gemm_4bit_wide(int batch, int N, int K, const T *A, const unsigned ch
     if (a.ws == nullptr) { a.splits = 1; a.kper = K; }
   }
   CUtensorMap tmX, tmW;
-  if (!make_tmap_2d(&tmX, A, 2, (uint64_t)batch, (uint64_t)K, (uint32_t)a.NB, TK, true, std::is_same<T, __nv_bfloat16>::value) ||
+  if (!make_tmap_2d(&tmX, A, 2, (uint64_t)batch, (uint64_t)K, (uint32_t)(pair ? a.NB / 2 : a.NB), TK, true, std::is_same<T, __nv_bfloat16>::value) ||
       !make_tmap_2d(&tmW, B, 1, (uint64_t)N, (uint64_t)(K / 2), TM, TK / 2, false, false, false)) {
     if (ws_from_pool) cudaFreeAsync(a.ws, st);
     return 2;
   }
   static int g_env = -1;   // BNB_B200_GEMM4_WIDE_G=3: three dequant groups at every width (A/B measurements)
   if (g_env < 0) { const char *e = getenv("BNB_B200_GEMM4_WIDE_G"); g_env = (e && e[0] == '3') ? 3 : 4; }
-  if (stages_for(a.NB) >= 4 && g_env == 4) {
-    ensure_max_dynamic_smem(reinterpret_cast<const void *>(k_gemm4_wide<T, 4>), kSmemBytes, "gemm_4bit wide smem attr");
-    k_gemm4_wide<T, 4><<<dim3(tiles, a.splits), threads_for(4), kSmemBytes, st>>>(tmX, tmW, a);
+  if (pair) {
+    ensure_max_dynamic_smem(reinterpret_cast<const void *>(k_gemm4_wide<T, 4, 2>), kSmemBytes, "gemm_4bit wide smem attr");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((tiles + 1) / 2 * 2, a.splits);
+    cfg.blockDim = dim3(threads_for(4));
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_gemm4_wide<T, 4, 2>, tmX, tmW, a);
+  } else if (stages_for(a.NB, 1) >= 4 && g_env == 4) {
+    ensure_max_dynamic_smem(reinterpret_cast<const void *>(k_gemm4_wide<T, 4, 1>), kSmemBytes, "gemm_4bit wide smem attr");
+    k_gemm4_wide<T, 4, 1><<<dim3(tiles, a.splits), threads_for(4), kSmemBytes, st>>>(tmX, tmW, a);
   } else {
-    ensure_max_dynamic_smem(reinterpret_cast<const void *>(k_gemm4_wide<T, 3>), kSmemBytes, "gemm_4bit wide smem attr");
-    k_gemm4_wide<T, 3><<<dim3(tiles, a.splits), threads_for(3), kSmemBytes, st>>>(tmX, tmW, a);
+    ensure_max_dynamic_smem(reinterpret_cast<const void *>(k_gemm4_wide<T, 3, 1>), kSmemBytes, "gemm_4bit wide smem attr");
+    k_gemm4_wide<T, 3, 1><<<dim3(tiles, a.splits), threads_for(3), kSmemBytes, st>>>(tmX, tmW, a);
   }
   check_launch("gemm_4bit (wide, tcgen05)");
   if (a.splits > 1) {

@@ -136,6 +136,48 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 
 }  // namespace tc
 
+// ---- CTA pairs (cluster of two CTAs on one TPC, tcgen05 cta_group::2) ------------------------------------------------
+// PTX forms as in the PTX ISA (cross-checked against cute/arch/copy_sm100_tma.hpp, cutlass/arch/barrier.h and
+// cute/arch/tmem_allocator_sm100.hpp of the CUTLASS headers inside the image's flashinfer package).
+namespace cg2 {
+__device__ __forceinline__ uint32_t cta_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address with the peer bit cleared = the even (leader) CTA of the pair
+// both CTAs of the pair load their own box; the bytes are counted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap *m, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the mbarrier at the same offset in BOTH CTAs once every MMA issued so far has completed
+__device__ __forceinline__ void umma_commit_both(uint32_t bar) {
+  asm volatile("{\n .reg .b16 m;\n mov.b16 m, 3;\n tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n}"
+               ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrive on the mbarrier at local address `bar` of CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile("{\n .reg .b32 r;\n mapa.shared::cluster.u32 r, %0, %1;\n mbarrier.arrive.shared::cluster.b64 _, [r];\n}"
+               ::"r"(bar), "r"(rank) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem] over the CTA pair: each CTA's TMEM holds its own 128 rows of A and receives its own 128 rows of D
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n}"
+               ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+}  // namespace cg2
+
 // host: build a 2-D tiled tensor map (row-major [rows, cols] of `elem_bytes` elements, box = box_cols x box_rows,
 // 128-byte swizzle).  Returns false (and latches an error) on failure.
 bool make_tmap_2d(CUtensorMap *map, const void *base, int elem_bytes, uint64_t rows, uint64_t cols, uint32_t box_rows,
