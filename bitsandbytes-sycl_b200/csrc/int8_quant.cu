@@ -295,11 +295,88 @@ __global__ void __launch_bounds__(256) k_transform_T(const E *__restrict__ A, E 
   out[layout_offset(FMT, out_rows, c, r)] = A[(long)r * cols + c];
 }
 
+
+// Tiled int8 layout kernels (rows % 32 == 0, cols % 32 == 0, 16-byte aligned buffers: every LLM.int8 shape).  In all three
+// layouts the block of (one 32-column panel) x (32 rows starting at a multiple of 32) is ONE contiguous kilobyte: col32 has
+// the 32 bytes of a row back to back, col_turing four 256-byte tiles of 8 rows, col_ampere one 1024-byte tile.  A CTA
+// moves 32 rows x 256 columns through shared memory: 16-byte accesses, fully coalesced on the row-major side (256 bytes
+// of a row per half-warp) AND on the layout side (a kilobyte per 64 threads), where the element-per-thread kernels
+// above wrote 4 bytes at a time into scattered sectors.  TO_ROW = false: row-major -> layout; true: layout -> row-major.
+constexpr int kLtRows = 32, kLtCols = 256, kLtPitch = kLtCols + 16;   // pitch keeps 16-byte alignment, spreads the banks
+template <int FMT, bool TO_ROW>
+__global__ void __launch_bounds__(256) k_layout_tiled(const signed char *__restrict__ src, signed char *__restrict__ dst, int rows,
+                                                      int cols, long lay_rows) {
+  __shared__ __align__(16) signed char tile[kLtRows][kLtPitch];
+  const int t = threadIdx.x;
+  const int c_base = blockIdx.x * kLtCols, r_base = blockIdx.y * kLtRows;
+  const int npanels = min(kLtCols, cols - c_base) >> 5;               // valid 32-column panels of this tile
+  const signed char *rm_c = TO_ROW ? nullptr : src;
+  signed char *rm = TO_ROW ? dst : const_cast<signed char *>(rm_c);    // the row-major buffer
+  // ---- row-major side: thread = (row t / 16 (+16), 16-byte chunk t % 16)
+  auto row_major_pass = [&](bool load) {
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int r = (t >> 4) + h * 16, ch = t & 15;
+      if ((ch >> 1) < npanels) {
+        signed char *g = rm + (long)(r_base + r) * cols + c_base + ch * 16;
+        uint4 *sm = reinterpret_cast<uint4 *>(&tile[r][ch * 16]);
+        if (load) *sm = *reinterpret_cast<const uint4 *>(g); else *reinterpret_cast<uint4 *>(g) = *sm;
+      }
+    }
+  };
+  // ---- layout side: panel p = piece / 64, 16-byte piece o16 = piece % 64 of its kilobyte
+  auto layout_pass = [&](bool load) {
+    const signed char *lay_c = TO_ROW ? src : nullptr;
+    signed char *lay = TO_ROW ? const_cast<signed char *>(lay_c) : dst;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int piece = t + h * 256;
+      const int p = piece >> 6, o = (piece & 63) * 16;
+      if (p >= npanels) continue;
+      signed char *g = lay + ((long)((c_base >> 5) + p) * lay_rows + r_base) * 32 + o;
+      if (FMT == COL_TURING) {
+        // 256-byte tile of 8 rows: bytes [0,128) even rows, [128,256) odd rows; 16 bytes = 4 rows x 4 columns
+        const int tile8 = o >> 8, o2 = o & 255, half = o2 >> 7, grp = (o2 & 127) >> 4;
+        uint32_t w[4];
+        if (load) {
+          const uint4 v = *reinterpret_cast<const uint4 *>(g);
+          w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          uint32_t *sm = reinterpret_cast<uint32_t *>(&tile[tile8 * 8 + 2 * j + half][p * 32 + grp * 4]);
+          if (load) *sm = w[j]; else w[j] = *sm;
+        }
+        if (!load) *reinterpret_cast<uint4 *>(g) = make_uint4(w[0], w[1], w[2], w[3]);
+      } else {
+        int r = o >> 5;                                                // col32: rows back to back
+        if (FMT == COL_AMPERE) r = (r >> 3) * 2 + (r & 1) + ((r >> 1) & 3) * 8;   // inverse of ar = ((lr & 7) >> 1) * 8 + (lr >> 3) * 2 + (lr & 1)
+        uint4 *sm = reinterpret_cast<uint4 *>(&tile[r][p * 32 + (o & 31)]);
+        if (load) *sm = *reinterpret_cast<const uint4 *>(g); else *reinterpret_cast<uint4 *>(g) = *sm;
+      }
+    }
+  };
+  if (TO_ROW) layout_pass(true); else row_major_pass(true);
+  __syncthreads();
+  if (TO_ROW) row_major_pass(false); else layout_pass(false);
+}
+static bool layout_tiled_ok(const void *a, const void *b, int rows, int cols) {
+  return rows % 32 == 0 && cols % 32 == 0 && (reinterpret_cast<uintptr_t>(a) % 16) == 0 && (reinterpret_cast<uintptr_t>(b) % 16) == 0 &&
+         rows / 32 <= 65535;
+}
+template <int FMT, bool TO_ROW>
+static void launch_layout_tiled(const signed char *src, signed char *dst, int rows, int cols) {
+  const dim3 grid((unsigned)ceil_div(cols, kLtCols), (unsigned)(rows / kLtRows));
+  k_layout_tiled<FMT, TO_ROW><<<grid, 256, 0, current_stream()>>>(src, dst, rows, cols, layout_out_rows(FMT, rows));
+}
+
 template <int FMT>
 void transform_row2fmt(const signed char *A, signed char *out, int rows, int cols, bool transpose) {
   if (rows <= 0 || cols <= 0) return;
   cudaStream_t st = current_stream();
-  if (!transpose) {
+  if (!transpose && layout_tiled_ok(A, out, rows, cols)) {
+    launch_layout_tiled<FMT, false>(A, out, rows, cols);
+  } else if (!transpose) {
     const long n = (long)rows * ((cols + 3) / 4);
     k_transform<FMT, signed char><<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(A, out, rows, cols, layout_out_rows(FMT, rows));
   } else {
@@ -327,6 +404,14 @@ __global__ void __launch_bounds__(256) k_untransform(const E *__restrict__ A, E 
     if (c + j < cols) dst[j] = src[j];
 }
 void untransform_s8(int fmt, const signed char *A, signed char *out, int rows, int cols) {
+  if (rows <= 0 || cols <= 0) return;
+  if (layout_tiled_ok(A, out, rows, cols)) {
+    if (fmt == COL32) launch_layout_tiled<COL32, true>(A, out, rows, cols);
+    else if (fmt == COL_TURING) launch_layout_tiled<COL_TURING, true>(A, out, rows, cols);
+    else launch_layout_tiled<COL_AMPERE, true>(A, out, rows, cols);
+    check_launch("untransform_s8 (tiled)");
+    return;
+  }
   const long n = (long)rows * ((cols + 3) / 4);
   const unsigned grid = (unsigned)ceil_div_ll(n, 256);
   cudaStream_t st = current_stream();

@@ -72,7 +72,7 @@ def test_double_quant_zero_row_and_column(F):
 
 
 @pytest.mark.parametrize("fmt", ["col32", "col_turing", "col_ampere"])
-@pytest.mark.parametrize("shape", [(32, 32), (7, 33), (40, 100), (129, 65), (256, 512)])
+@pytest.mark.parametrize("shape", [(32, 32), (7, 33), (40, 100), (129, 65), (256, 512), (64, 288), (96, 1056), (2048, 1024)])   # the last four: tiled kernel
 @pytest.mark.parametrize("transpose", [False, True])
 def test_transforms_bit_exact(F, fmt, shape, transpose):
     rng = np.random.RandomState(shape[0])
@@ -467,7 +467,7 @@ def test_int8_linear_fused_config3_paths_vs_oracle(F, k, m, n_outlier_cols):
 
 
 @pytest.mark.parametrize("fmt", ["col32", "col_turing", "col_ampere"])
-@pytest.mark.parametrize("shape", [(64, 64), (37, 300), (512, 4096)])
+@pytest.mark.parametrize("shape", [(64, 64), (37, 300), (512, 4096), (96, 288), (32, 1056)])
 def test_inverse_layout_transforms(F, fmt, shape):
     """ctransform_{col32,turing,ampere}2row (the reference's Python calls the last two at functional.py:2645-2647):
     row -> layout -> row is the identity, and the device inverse agrees with the host-side undo_layout_to_row."""
