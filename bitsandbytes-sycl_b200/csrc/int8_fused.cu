@@ -128,13 +128,19 @@ __global__ void __launch_bounds__(256) k_i8_quant_rows(const __half *__restrict_
 // K <= NV * 256: the whole row lives in registers (NV 128-bit loads in flight per lane), so statistics and quantisation
 // are ONE pass over A.  Outlier COLUMNS are not known yet (they depend on every row): CA is written for all columns and
 // k_i8_fix_outliers zeroes the (few) outlier columns afterwards.
+// rint + saturate to int8 in one instruction (same result as quant_s8_: rint, then clamp; NaN -> 0)
+__device__ __forceinline__ uint32_t f2s8_sat_(float x) {
+  int q;
+  asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(q) : "f"(x));
+  return (uint32_t)q;
+}
 template <int NV>
-__global__ void __launch_bounds__(256) k_i8_row_onepass(const __half *__restrict__ A, float *__restrict__ rowStats,
+__global__ void __launch_bounds__(128) k_i8_row_onepass(const __half *__restrict__ A, float *__restrict__ rowStats,
                                                         unsigned char *__restrict__ colflag, signed char *__restrict__ CA,
                                                         float thr, int rows, int cols) {
   pdl_enter();
   const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);      // four rows per CTA: 1024 small CTAs backfill the SMs evenly
   if (r >= rows) return;
   const __half *row = A + (size_t)r * cols;
   uint4 raw[NV];
@@ -146,13 +152,25 @@ __global__ void __launch_bounds__(256) k_i8_row_onepass(const __half *__restrict
   float rmax = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; i++) {
-    const int c0 = (i * 32 + lane) * 8;
-    const __half *p = reinterpret_cast<const __half *>(&raw[i]);
+    // |x| of eight halves in four packed operations, their maximum in three more (exact in fp16); only a chunk that
+    // holds an outlier (max >= thr, compared in fp32 like the reference) takes the per-element path
+    const uint32_t a0 = raw[i].x & 0x7FFF7FFFu, a1 = raw[i].y & 0x7FFF7FFFu, a2 = raw[i].z & 0x7FFF7FFFu, a3 = raw[i].w & 0x7FFF7FFFu;
+    const __half2 m01 = __hmax2(*reinterpret_cast<const __half2 *>(&a0), *reinterpret_cast<const __half2 *>(&a1));
+    const __half2 m23 = __hmax2(*reinterpret_cast<const __half2 *>(&a2), *reinterpret_cast<const __half2 *>(&a3));
+    const __half2 m = __hmax2(m01, m23);
+    const float cm = fmaxf(__low2float(m), __high2float(m));
+    // (NaN: __hmax2 returns the other operand, fmaxf likewise -- ignored exactly as in the per-element path)
+    if (cm >= thr) {
+      const int c0 = (i * 32 + lane) * 8;
+      const __half *p = reinterpret_cast<const __half *>(&raw[i]);
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      float v = fabsf(__half2float(p[j]));
-      if (v >= thr) { colflag[c0 + j] = 1; v = 0.f; }
-      rmax = fmaxf(rmax, v);
+      for (int j = 0; j < 8; j++) {
+        float v = fabsf(__half2float(p[j]));
+        if (v >= thr) { colflag[c0 + j] = 1; v = 0.f; }
+        rmax = fmaxf(rmax, v);
+      }
+    } else {
+      rmax = fmaxf(rmax, cm);
     }
   }
 #pragma unroll
@@ -163,10 +181,15 @@ __global__ void __launch_bounds__(256) k_i8_row_onepass(const __half *__restrict
   for (int i = 0; i < NV; i++) {
     const int c0 = (i * 32 + lane) * 8;
     if (c0 >= cols) continue;
-    const __half *p = reinterpret_cast<const __half *>(&raw[i]);
-    uint32_t q[2] = {0, 0};
+    const __half2 *p2 = reinterpret_cast<const __half2 *>(&raw[i]);
+    uint32_t q[2];
 #pragma unroll
-    for (int j = 0; j < 8; j++) q[j >> 2] |= (uint32_t)(quant_s8_(__half2float(p[j]), scale) & 0xFF) << (8 * (j & 3));
+    for (int h = 0; h < 2; h++) {
+      const float2 f0 = __half22float2(p2[2 * h]), f1 = __half22float2(p2[2 * h + 1]);
+      const uint32_t b0 = f2s8_sat_(__fmul_rn(f0.x, scale)), b1 = f2s8_sat_(__fmul_rn(f0.y, scale));
+      const uint32_t b2 = f2s8_sat_(__fmul_rn(f1.x, scale)), b3 = f2s8_sat_(__fmul_rn(f1.y, scale));
+      q[h] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+    }
     *reinterpret_cast<uint2 *>(CA + (size_t)r * cols + c0) = make_uint2(q[0], q[1]);
   }
 }
@@ -243,9 +266,10 @@ int int8_linear_fused(const __half *A, const signed char *CB, const float *SCB, 
   const dim3 rows8((unsigned)ceil_div(m, 8)), b256(256);
   if (k <= 4096) {
     // one pass over A: the row stays in registers between the statistics and the quantisation
-    if (k <= 1024) launch_pdl(k_i8_row_onepass<4>, rows8, b256, st, A, SCA, colflag, CA, thr, m, k);
-    else if (k <= 2048) launch_pdl(k_i8_row_onepass<8>, rows8, b256, st, A, SCA, colflag, CA, thr, m, k);
-    else launch_pdl(k_i8_row_onepass<16>, rows8, b256, st, A, SCA, colflag, CA, thr, m, k);
+    const dim3 rows4((unsigned)((m + 3) / 4)), b128(128);
+    if (k <= 1024) launch_pdl(k_i8_row_onepass<4>, rows4, b128, st, A, SCA, colflag, CA, thr, m, k);
+    else if (k <= 2048) launch_pdl(k_i8_row_onepass<8>, rows4, b128, st, A, SCA, colflag, CA, thr, m, k);
+    else launch_pdl(k_i8_row_onepass<16>, rows4, b128, st, A, SCA, colflag, CA, thr, m, k);
     launch_pdl(k_i8_compact, dim3(1), dim3(1024), st, colflag, idx, pos, count, k, idx_cap);
     launch_pdl(k_i8_fix_outliers, dim3(kNumSMs), b256, st, A, CA, subA, idx, count, m, k, idx_cap);
   } else {
