@@ -296,10 +296,11 @@ def quantize_blockwise(A: Tensor, code: Optional[Tensor] = None, absmax: Optiona
             name2qmap["dynamic"] = create_dynamic_map().to(A.device)
         code = name2qmap["dynamic"]
     n = A.numel()
+    # the kernel writes every block's absmax and every code byte: no zero fill (the reference allocates with torch.zeros)
     if absmax is None:
-        absmax = torch.zeros(((n + blocksize - 1) // blocksize,), device=A.device, dtype=torch.float32)
+        absmax = torch.empty(((n + blocksize - 1) // blocksize,), device=A.device, dtype=torch.float32)
     if out is None:
-        out = torch.zeros_like(A, dtype=torch.uint8)
+        out = torch.empty_like(A, dtype=torch.uint8)
     assert blocksize in _BLOCKSIZES
     if A.dtype not in _SUFFIX:
         raise ValueError(f"Blockwise quantization only supports 16/32-bit floats, but got {A.dtype}")
@@ -380,10 +381,12 @@ def quantize_4bit(A: Tensor, absmax: Optional[Tensor] = None, out: Optional[Tens
     n = A.numel()
     input_shape = A.shape
     if absmax is None:
-        absmax = torch.zeros(((n + blocksize - 1) // blocksize,), device=A.device, dtype=torch.float32)
+        absmax = torch.empty(((n + blocksize - 1) // blocksize,), device=A.device, dtype=torch.float32)
     if out is None:
         mod = dtype2bytes[quant_storage] * 2
-        out = torch.zeros(((n + 1) // mod, 1), dtype=quant_storage, device=A.device)
+        # every packed byte is written when the storage is bytes and n is even; otherwise the tail must read as zero
+        alloc = torch.empty if (quant_storage == torch.uint8 and n % 2 == 0) else torch.zeros
+        out = alloc(((n + 1) // mod, 1), dtype=quant_storage, device=A.device)
     assert blocksize in _BLOCKSIZES
     if A.dtype not in _SUFFIX:
         raise ValueError(f"Blockwise quantization only supports 16/32-bit floats, but got {A.dtype}")
@@ -745,10 +748,10 @@ def double_quant(A, col_stats=None, row_stats=None, out_col=None, out_row=None, 
     nnz_row_ptr = None
     if row_stats is None or col_stats is None:
         row_stats, col_stats, nnz_row_ptr = get_colrow_absmax(A, threshold=threshold)
-    if out_col is None:
-        out_col = torch.zeros(A.shape, device=device, dtype=torch.int8)
+    if out_col is None:      # every element of both outputs is written by the kernel
+        out_col = torch.empty(A.shape, device=device, dtype=torch.int8)
     if out_row is None:
-        out_row = torch.zeros(A.shape, device=device, dtype=torch.int8)
+        out_row = torch.empty(A.shape, device=device, dtype=torch.int8)
     A = A.contiguous()
     coo_tensor = None
     args = [get_ptr(A), get_ptr(row_stats), get_ptr(col_stats), get_ptr(out_col), get_ptr(out_row)]
