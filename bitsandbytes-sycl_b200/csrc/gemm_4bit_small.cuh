@@ -1,19 +1,22 @@
-// gemm_4bit_small.cuh -- batch 9..64 route of the fused 4-bit GEMM (included by gemm_4bit.cu).
+// gemm_4bit_small.cuh -- batch <= 32 route of the fused 4-bit GEMM (included by gemm_4bit.cu).
 //
-// The general kernel (k_gemm4_tcgen05) dequantises every weight with the reference's arithmetic -- two table lookups,
-// two fp32 multiplies by absmax, one conversion per packed byte -- and at batch <= 64, where the tile is HBM-bound, those
-// ~9 thread-instructions per weight are the whole cost (ncu: issue 47 %, tensor pipe 3 %).  Here the per-block scale
-// leaves the per-weight path:
-//   * the UMMA A operand is the UNSCALED code value T(code[q]): one PRMT + one conflict-free LDS per packed byte out of
-//     the lane-replicated byte-pair table of the GEMV, one STS.128 per eight weights (~1.2 instructions per weight);
+// At these widths the tile is HBM-bound and what the kernel spends is instructions per weight.  The per-block scale
+// therefore leaves the per-weight path:
+//   * the UMMA A operand is the UNSCALED code value T(code[q]): one PRMT + one conflict-free LDS per packed byte out of a
+//     lane-replicated byte-pair table (64 KB, on a 64 KB boundary of the shared window so that the PRMT result IS the
+//     address), 32 registers per thread and stage written straight to TENSOR MEMORY with one tcgen05.st.32x32b.x32
+//     (thread = TMEM lane = weight row); the MMA takes A from TMEM -- one instruction per weight element in all;
 //   * a stage is exactly one quantisation block of every row (64 k-elements, blocksize 64; a larger blocksize spans
 //     whole stages), accumulated by four tcgen05.mma into its OWN slot of a ring of TMEM accumulators;
-//   * four "scaler" warps (thread = TMEM lane = weight row) lift a finished slot out of TMEM, multiply it by the fp32
+//   * "scaler" warps (thread = TMEM lane = weight row) lift a finished slot out of TMEM, multiply it by the fp32
 //     absmax of (row, block) and add it to fp32 totals kept in registers: batch FMAs per row per block instead of 64
 //     multiplies -- and code * absmax is never rounded to T, so the result is closer to the exact product than the
 //     reference's dequantize-then-matmul (tests compare with both).
-// Persistent CTAs (one per SM) walk (128-row tile, K split) units; split-K partials go to the fp32 workspace of the
-// general kernel and are summed by k_gemm4_finalize in split order.
+// Warps: 0 packed-weight TMA | 1, 3 MMA issue for even / odd stages | 2 activation TMA | 4..15 dequant (three groups of
+// four) | 16.. scalers.  One mbarrier per stage collects everything the MMA needs, one tcgen05.commit per stage frees the
+// operands and publishes the accumulator.  Persistent CTAs (one per SM) walk (128-row tile, K split) units; split-K
+// partials go to the fp32 workspace of gemm_4bit.cu and are summed by k_gemm4_finalize in split order.
+// Measurements, the role traces and the variants that lost are in profiles/r2_gemm4_small_roles.md.
 #pragma once
 
 namespace g4s {
@@ -42,7 +45,7 @@ __host__ __device__ constexpr int stages_for(int NB, int KB) { return KB == 2 ? 
 
 struct Args {
   int batch, N, K, bs_shift;
-  int NB;            // UMMA N: batch rounded up to 16 (<= 64)
+  int NB;            // UMMA N: batch rounded up to 16 (16 or 32 as dispatched; the kernel itself is generic up to 64)
   int splits, kper;  // K elements per split (multiple of 64 * KB)
   int tiles;         // 128-row tiles
   const unsigned char *B;
