@@ -599,11 +599,15 @@ def gemv_4bit_multi(A: Tensor, Bs, states, outs=None, peer_outs=None):
 
 
 def gemm_4bit(A: Tensor, B: Tensor, state: QuantState, bias: Optional[Tensor] = None,
-              out: Optional[Tensor] = None) -> Optional[Tensor]:
+              out: Optional[Tensor] = None, peer_outs: Optional[List[int]] = None) -> Optional[Tensor]:
     """ADDITIVE: fused batch>1 4-bit GEMM, out[b, N] = A[b, K] @ T(dequant(B))^T (+bias) without ever
     materialising the dequantised weight (tcgen05 kind::f16, TMEM accumulators).  Returns None when the
     native kernel does not take the shape -- the caller then runs the reference route
-    (dequantize_4bit + F.linear, autograd/_functions.py:507)."""
+    (dequantize_4bit + F.linear, autograd/_functions.py:507).
+
+    N-sharded stacks (bnb_b200/parallel.py): `out` may be a [batch, N] column slice of a wider row-major buffer (row stride
+    out.stride(0)), and `peer_outs` the device addresses of the same slice in the peers' copies of that buffer (NVLink peer
+    mappings): the epilogue stores into all of them (cgemm_4bit_push_*)."""
     if not FUSED_GEMM_4BIT or A.dtype not in (torch.float16, torch.bfloat16):
         return None
     if state.dtype not in (A.dtype, torch.float32):
@@ -615,7 +619,11 @@ def gemm_4bit(A: Tensor, B: Tensor, state: QuantState, bias: Optional[Tensor] = 
         return None     # wrong activation width: the reference route raises the shape error of F.linear
     A2 = A.reshape(-1, A.shape[-1]).contiguous()
     batch = A2.shape[0]
-    if (2 <= batch <= 8 and bias is None and state.nested and FUSED_NESTED_GEMV and K % 64 == 0 and N % 16 == 0
+    strided = out is not None and (out.dim() != 2 or tuple(out.shape) != (batch, N) or out.stride(1) != 1 or out.stride(0) != N)
+    if strided and (out.dim() != 2 or tuple(out.shape) != (batch, N) or out.stride(1) != 1 or out.dtype != A.dtype):
+        raise ValueError("gemm_4bit: out must be a [batch, N] view with unit column stride and the dtype of A")
+    push = strided or bool(peer_outs)
+    if (not push and 2 <= batch <= 8 and bias is None and state.nested and FUSED_NESTED_GEMV and K % 64 == 0 and N % 16 == 0
             and state.blocksize % 64 == 0 and A2.shape[1] == K and B.dtype == torch.uint8):
         # batch 2..8: the batch rides in the MMA's n dimension of the LUT + mma.sync GEMV kernels (nested absmax read
         # directly, fp32 absmax applied to fp32 partial sums): ~1.8x faster than the tcgen05 kernel at these sizes
@@ -649,13 +657,22 @@ def gemm_4bit(A: Tensor, B: Tensor, state: QuantState, bias: Optional[Tensor] = 
     b = None if bias is None else bias.to(A.dtype).contiguous()
     prev = pre_call(A.device)
     is_on_gpu([A2, B, absmax, code, out, b])
-    rc = getattr(lib, f"cgemm_4bit_{_SUFFIX[A.dtype]}")(
-        ct.c_int32(batch), ct.c_int32(N), ct.c_int32(K), get_ptr(A2), get_ptr(B), get_ptr(absmax), get_ptr(code),
-        get_ptr(b), get_ptr(out), ct.c_int32(state.blocksize))
+    if push:
+        peer_outs = list(peer_outs or [])
+        if len(peer_outs) > 7:
+            raise ValueError("gemm_4bit: at most 7 peers")
+        parr = (ct.c_void_p * max(len(peer_outs), 1))(*[ct.c_void_p(int(p)) for p in peer_outs])
+        rc = getattr(lib, f"cgemm_4bit_push_{_SUFFIX[A.dtype]}")(
+            ct.c_int32(batch), ct.c_int32(N), ct.c_int32(K), get_ptr(A2), get_ptr(B), get_ptr(absmax), get_ptr(code),
+            get_ptr(b), get_ptr(out), ct.c_int32(state.blocksize), ct.c_long(out.stride(0)), parr, ct.c_int32(len(peer_outs)))
+    else:
+        rc = getattr(lib, f"cgemm_4bit_{_SUFFIX[A.dtype]}")(
+            ct.c_int32(batch), ct.c_int32(N), ct.c_int32(K), get_ptr(A2), get_ptr(B), get_ptr(absmax), get_ptr(code),
+            get_ptr(b), get_ptr(out), ct.c_int32(state.blocksize))
     post_call(prev)
     if rc != 0:
         return None
-    return out.reshape(*A.shape[:-1], N)
+    return out if push else out.reshape(*A.shape[:-1], N)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -96,31 +96,35 @@ class PeerOutputBuffers:
     `barrier()` (symmetric-memory signal-pad barrier, one small kernel) is what a consumer of the gathered
     vectors waits on."""
 
-    def __init__(self, sizes: List[int], dtype: torch.dtype, device: torch.device, group=None):
+    def __init__(self, sizes: List[int], dtype: torch.dtype, device: torch.device, group=None, batch: int = 1):
         import torch.distributed._symmetric_memory as symm_mem
 
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self.sizes = list(sizes)
+        self.batch = int(batch)                  # rows of every gathered output ([batch, N_i], row-major)
         self.offsets = []
         off = 0
         for n in self.sizes:
             assert n % self.world == 0
             self.offsets.append(off)
-            off += (n + 63) // 64 * 64           # keep every vector 128-byte aligned
+            off += (self.batch * n + 63) // 64 * 64   # keep every output 128-byte aligned
         self.buf = symm_mem.empty(max(off, 64), dtype=dtype, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         self.itemsize = self.buf.element_size()
         self.base_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
 
     def full(self, i: int) -> torch.Tensor:
-        return self.buf[self.offsets[i]:self.offsets[i] + self.sizes[i]].view(1, -1)
+        return self.buf[self.offsets[i]:self.offsets[i] + self.batch * self.sizes[i]].view(self.batch, self.sizes[i])
 
     def local_slice(self, i: int) -> torch.Tensor:
+        """This rank's columns of output i: [batch, N_i / world], row stride N_i (contiguous when batch == 1)."""
         per = self.sizes[i] // self.world
-        o = self.offsets[i] + self.rank * per
-        return self.buf[o:o + per].view(1, per)
+        if self.batch == 1:
+            o = self.offsets[i] + self.rank * per
+            return self.buf[o:o + per].view(1, per)
+        return self.full(i)[:, self.rank * per:(self.rank + 1) * per]
 
     def peer_ptrs(self, i: int) -> List[int]:
         per = self.sizes[i] // self.world
@@ -198,6 +202,16 @@ def sharded_gemv_push(x: torch.Tensor, packed_shard: torch.Tensor, state_shard: 
     """Rank-local GEMV of linear i whose epilogue stores the output slice into every rank's full vector."""
     return F.gemv_4bit(x, packed_shard.t(), out=peers.local_slice(i), state=state_shard, peer_outs=peers.peer_ptrs(i),
                        sync=sync)
+
+
+def sharded_gemm_push(x: torch.Tensor, packed_shard: torch.Tensor, state_shard: QuantState, peers: PeerOutputBuffers,
+                      i: int, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Batch > 1: rank-local fused 4-bit GEMM of linear i whose epilogue stores the [batch, N_i / world] slice into every
+    rank's gathered [batch, N_i] buffer (functional.gemm_4bit with peer outputs -> cgemm_4bit_push_*)."""
+    y = F.gemm_4bit(x, packed_shard.t(), state_shard, bias=bias, out=peers.local_slice(i), peer_outs=peers.peer_ptrs(i))
+    if y is None:
+        raise RuntimeError("sharded_gemm_push: the fused kernel does not take this shape")
+    return y
 
 
 def sharded_gemv_push_multi(x: torch.Tensor, packed_shards, state_shards, peers: PeerOutputBuffers, idxs) -> list:

@@ -51,7 +51,7 @@ struct GemvSync;
 void epoch_bump(unsigned int *epoch);
 void peer_barrier(unsigned int *counter, const unsigned int *sig_local, unsigned int *const *sig_peer, int npeers);
 template <typename T> void gemv_4bit_nested(int, int, int, const T *, const unsigned char *, const unsigned char *, const float *, const float *, float, const float *, T *, int, int, int, int, int, void *const *, int, const GemvSync *);
-template <typename T> int gemm_4bit(int, int, int, const T *, const unsigned char *, const float *, const float *, const T *, T *, int);
+template <typename T> int gemm_4bit(int, int, int, const T *, const unsigned char *, const float *, const float *, const T *, T *, int, long, void *const *, int);
 void get_col_row_stats(const __half *, float *, float *, int *, float, int, int);
 void double_rowcol_quant(const __half *, const float *, const float *, signed char *, signed char *, int *, int *, __half *, const int *, float, int, int);
 template <int FMT> void transform_row2fmt(const signed char *, signed char *, int, int, bool);
@@ -140,9 +140,15 @@ void cbnb_peer_barrier(unsigned int *counter, const unsigned int *sig_local, uns
 
 // ---------------------------------------------------------------- fused 4-bit GEMM (additive)
 int cgemm_4bit_fp16(int batch, int N, int K, void *A, unsigned char *B, float *absmax, float *datatype, void *bias, void *out, int blocksize) {
-  return gemm_4bit<half_t>(batch, N, K, (half_t *)A, B, absmax, datatype, (half_t *)bias, (half_t *)out, blocksize); }
+  return gemm_4bit<half_t>(batch, N, K, (half_t *)A, B, absmax, datatype, (half_t *)bias, (half_t *)out, blocksize, 0, nullptr, 0); }
 int cgemm_4bit_bf16(int batch, int N, int K, void *A, unsigned char *B, float *absmax, float *datatype, void *bias, void *out, int blocksize) {
-  return gemm_4bit<bf16_t>(batch, N, K, (bf16_t *)A, B, absmax, datatype, (bf16_t *)bias, (bf16_t *)out, blocksize); }
+  return gemm_4bit<bf16_t>(batch, N, K, (bf16_t *)A, B, absmax, datatype, (bf16_t *)bias, (bf16_t *)out, blocksize, 0, nullptr, 0); }
+// N-sharded form: `out` is the base of this rank's column slice inside the gathered [batch, ldo] buffer, peer_outs the same
+// address in every peer's copy (NVLink peer mappings); the epilogue stores into all of them
+int cgemm_4bit_push_fp16(int batch, int N, int K, void *A, unsigned char *B, float *absmax, float *datatype, void *bias, void *out, int blocksize, long ldo, void **peer_outs, int npeers) {
+  return gemm_4bit<half_t>(batch, N, K, (half_t *)A, B, absmax, datatype, (half_t *)bias, (half_t *)out, blocksize, ldo, peer_outs, npeers); }
+int cgemm_4bit_push_bf16(int batch, int N, int K, void *A, unsigned char *B, float *absmax, float *datatype, void *bias, void *out, int blocksize, long ldo, void **peer_outs, int npeers) {
+  return gemm_4bit<bf16_t>(batch, N, K, (bf16_t *)A, B, absmax, datatype, (bf16_t *)bias, (bf16_t *)out, blocksize, ldo, peer_outs, npeers); }
 
 // ---------------------------------------------------------------- LLM.int8 (pythonInterface.cpp:333-369)
 void cget_col_row_stats(void *A, float *rowStats, float *colStats, int *nnz_count_row, float nnz_threshold, int rows, int cols) {

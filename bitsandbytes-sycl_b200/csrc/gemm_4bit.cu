@@ -30,6 +30,16 @@ namespace g4 {
 constexpr int TK = 64;             // K elements per stage (one quantisation block of blocksize 64)
 constexpr int kMaxNB = 256;
 
+// Where the result goes.  ldo = elements between consecutive batch rows of `out` (N for a plain call).  N-sharded stacks
+// (bnb_b200/parallel.py) pass the base of this rank's column slice inside the gathered [batch, N_total] buffer, ldo =
+// N_total, and the same address in every peer's copy of the buffer (NVLink peer mappings): the epilogue then IS the
+// all-gather, as in the batch-1 GEMV (cgemm_4bit_inference_nested_push_*).
+struct OutSpec {
+  long ldo;
+  int npeers;
+  void *peer[7];
+};
+
 template <typename T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
 template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
@@ -48,13 +58,18 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
 // split-K: out[b, n] = T(sum_s ws[s, b, n] + bias[n]), summed in split order (deterministic)
 template <typename T>
 __global__ void __launch_bounds__(256) k_gemm4_finalize(const float *__restrict__ ws, const T *__restrict__ bias, T *__restrict__ out,
-                                                        int splits, int batch, int N) {
+                                                        int splits, int batch, int N, const OutSpec o) {
   const size_t total = (size_t)batch * N;
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
     float s = 0.f;
     for (int k = 0; k < splits; k++) s = __fadd_rn(s, ws[(size_t)k * total + i]);
-    if (bias != nullptr) s = __fadd_rn(s, to_float<T>(bias[i % N]));
-    out[i] = from_float<T>(s);
+    const size_t b = i / N, n = i % N;
+    if (bias != nullptr) s = __fadd_rn(s, to_float<T>(bias[n]));
+    const T v = from_float<T>(s);
+    out[b * o.ldo + n] = v;
+#pragma unroll
+    for (int p = 0; p < 7; p++)
+      if (p < o.npeers) reinterpret_cast<T *>(o.peer[p])[b * o.ldo + n] = v;
   }
 }
 
@@ -96,8 +111,13 @@ static int ilog2_(int v) { int s = 0; while ((1 << s) < v) s++; return s; }
 // returns 0 ok, 1 shape not taken by the fused kernel (caller uses dequantize + matmul), 2 error
 template <typename T>
 int gemm_4bit(int batch, int N, int K, const T *A, const unsigned char *B, const float *absmax, const float *datatype,
-              const T *bias, T *out, int blocksize) {
+              const T *bias, T *out, int blocksize, long ldo, void *const *peer_outs, int npeers) {
   using namespace g4;
+  if (npeers < 0 || npeers > 7 || (ldo != 0 && ldo < N)) { latch_error(cudaErrorInvalidValue, "gemm_4bit: bad output spec"); return 2; }
+  OutSpec ospec{};
+  ospec.ldo = ldo ? ldo : N;
+  ospec.npeers = npeers;
+  for (int i = 0; i < npeers; i++) ospec.peer[i] = peer_outs[i];
   if (batch <= 0 || N <= 0) return 0;
   if (batch > kMaxNB || K < TK || (K % TK) != 0 || blocksize < 64 || (blocksize & (blocksize - 1)) != 0 ||
       (reinterpret_cast<uintptr_t>(A) % 16) != 0 || (reinterpret_cast<uintptr_t>(B) % 32) != 0 || ((K / 2) % 32) != 0)
@@ -114,12 +134,12 @@ int gemm_4bit(int batch, int N, int K, const T *A, const unsigned char *B, const
   static int small_off = -1;   // BNB_B200_GEMM4_SMALL=0: the wide kernel at every batch (A/B measurements)
   if (small_off < 0) { const char *e = getenv("BNB_B200_GEMM4_SMALL"); small_off = (e && e[0] == '0') ? 1 : 0; }
   if (batch <= 32 && !small_off && K / TK >= 8)
-    return gemm_4bit_small<T>(batch, N, K, A, B, absmax, datatype, bias, out, ilog2_(blocksize), num_sms[dev], dev, st);
+    return gemm_4bit_small<T>(batch, N, K, A, B, absmax, datatype, bias, out, ilog2_(blocksize), num_sms[dev], dev, st, ospec);
   if (K / TK < 4) return 1;
-  return gemm_4bit_wide<T>(batch, N, K, A, B, absmax, datatype, bias, out, ilog2_(blocksize), num_sms[dev], dev, st);
+  return gemm_4bit_wide<T>(batch, N, K, A, B, absmax, datatype, bias, out, ilog2_(blocksize), num_sms[dev], dev, st, ospec);
 }
 
-template int gemm_4bit<__half>(int, int, int, const __half *, const unsigned char *, const float *, const float *, const __half *, __half *, int);
-template int gemm_4bit<__nv_bfloat16>(int, int, int, const __nv_bfloat16 *, const unsigned char *, const float *, const float *, const __nv_bfloat16 *, __nv_bfloat16 *, int);
+template int gemm_4bit<__half>(int, int, int, const __half *, const unsigned char *, const float *, const float *, const __half *, __half *, int, long, void *const *, int);
+template int gemm_4bit<__nv_bfloat16>(int, int, int, const __nv_bfloat16 *, const unsigned char *, const float *, const float *, const __nv_bfloat16 *, __nv_bfloat16 *, int, long, void *const *, int);
 
 }  // namespace bnb

@@ -54,6 +54,7 @@ struct Args {
   const void *bias;  // T[N] or null
   void *out;         // T[batch, N]           (splits == 1)
   float *ws;         // fp32 [splits, batch, N] (splits > 1)
+  g4::OutSpec o;     // row stride of out, peer copies (N-sharded stacks)
 #ifdef G4S_TRACE
   int dbg;           // trace build only: 1 skip the dequant work, 2 skip the MMAs, 4 skip the TMEM loads
 #endif
@@ -414,7 +415,13 @@ __global__ void __launch_bounds__(threads_for(NB16 * 16), 1) k_gemm4_small(const
         for (int j = 0; j < HC; j++) {
           const int b = col0 + j;
           if (b < a.batch) {
-            if (a.splits == 1) reinterpret_cast<T *>(a.out)[(size_t)b * a.N + orow] = from_float<T>(__fadd_rn(tot[j], bias));
+            if (a.splits == 1) {
+              const T v = from_float<T>(__fadd_rn(tot[j], bias));
+              reinterpret_cast<T *>(a.out)[(size_t)b * a.o.ldo + orow] = v;
+#pragma unroll
+              for (int p = 0; p < 7; p++)                                  // NVLink peer stores: the all-gather of an N-sharded stack
+                if (p < a.o.npeers) reinterpret_cast<T *>(a.o.peer[p])[(size_t)b * a.o.ldo + orow] = v;
+            }
             else a.ws[((size_t)split * a.batch + b) * a.N + orow] = tot[j];
           }
         }
@@ -433,12 +440,12 @@ __global__ void __launch_bounds__(threads_for(NB16 * 16), 1) k_gemm4_small(const
 // host: batch <= 32.  returns 0 ok, 2 error
 template <typename T>
 static int gemm_4bit_small(int batch, int N, int K, const T *A, const unsigned char *B, const float *absmax, const float *datatype,
-                           const T *bias, T *out, int bs_shift, int sms, int dev, cudaStream_t st) {
+                           const T *bias, T *out, int bs_shift, int sms, int dev, cudaStream_t st, const g4::OutSpec &ospec) {
   using namespace g4s;
   Args a{};
   a.batch = batch; a.N = N; a.K = K; a.bs_shift = bs_shift;
   a.NB = (batch + 15) / 16 * 16;
-  a.B = B; a.absmax = absmax; a.code = datatype; a.bias = bias; a.out = out;
+  a.B = B; a.absmax = absmax; a.code = datatype; a.bias = bias; a.out = out; a.o = ospec;
   a.tiles = (N + TM - 1) / TM;
 #ifdef G4S_TRACE
   { const char *e = getenv("G4S_DBG"); a.dbg = e ? atoi(e) : 0; }
@@ -490,7 +497,7 @@ static int gemm_4bit_small(int batch, int N, int K, const T *A, const unsigned c
     const size_t total = (size_t)batch * N;
     int blocks = (int)((total + 255) / 256);
     if (blocks > sms * 8) blocks = sms * 8;
-    g4::k_gemm4_finalize<T><<<blocks, 256, 0, st>>>(a.ws, bias, out, a.splits, batch, N);
+    g4::k_gemm4_finalize<T><<<blocks, 256, 0, st>>>(a.ws, bias, out, a.splits, batch, N, ospec);
     check_launch("gemm_4bit (finalize)");
     if (ws_from_pool) cudaFreeAsync(a.ws, st);
   }

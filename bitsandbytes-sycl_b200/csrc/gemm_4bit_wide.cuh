@@ -42,6 +42,7 @@ struct Args {
   const void *bias;  // T[N] or null
   void *out;         // T[batch, N]           (splits == 1)
   float *ws;         // fp32 [splits, batch, N] (splits > 1)
+  g4::OutSpec o;     // row stride of out, peer copies (N-sharded stacks)
 };
 
 __device__ __forceinline__ float2 lds64f(uint32_t saddr) {
@@ -240,7 +241,13 @@ __global__ void __launch_bounds__(threads_for(G), 1) k_gemm4_wide(const __grid_c
           const int b = c0 + j;
           if (b < a.batch) {
             const float acc = __uint_as_float(v[j]);
-            if (a.splits == 1) reinterpret_cast<T *>(a.out)[(size_t)b * a.N + orow] = from_float<T>(__fadd_rn(acc, bias));
+            if (a.splits == 1) {
+              const T v = from_float<T>(__fadd_rn(acc, bias));
+              reinterpret_cast<T *>(a.out)[(size_t)b * a.o.ldo + orow] = v;
+#pragma unroll
+              for (int p = 0; p < 7; p++)                                  // NVLink peer stores: the all-gather of an N-sharded stack
+                if (p < a.o.npeers) reinterpret_cast<T *>(a.o.peer[p])[(size_t)b * a.o.ldo + orow] = v;
+            }
             else a.ws[((size_t)split * a.batch + b) * a.N + orow] = acc;
           }
         }
@@ -257,7 +264,7 @@ __global__ void __launch_bounds__(threads_for(G), 1) k_gemm4_wide(const __grid_c
 // host: returns 0 ok, 2 error
 template <typename T>
 static int gemm_4bit_wide(int batch, int N, int K, const T *A, const unsigned char *B, const float *absmax, const float *datatype,
-                          const T *bias, T *out, int bs_shift, int sms, int dev, cudaStream_t st) {
+                          const T *bias, T *out, int bs_shift, int sms, int dev, cudaStream_t st, const g4::OutSpec &ospec) {
   using namespace g4w;
   Args a{};
   a.batch = batch; a.N = N; a.K = K; a.bs_shift = bs_shift;
@@ -266,7 +273,7 @@ static int gemm_4bit_wide(int batch, int N, int K, const T *A, const unsigned ch
   const int tiles = (N + TM - 1) / TM;
   const bool pair = pair_min > 0 && batch >= pair_min && tiles >= 2;
   a.NB = pair ? (batch + 31) / 32 * 32 : (batch + 15) / 16 * 16;
-  a.B = B; a.absmax = absmax; a.code = datatype; a.bias = bias; a.out = out;
+  a.B = B; a.absmax = absmax; a.code = datatype; a.bias = bias; a.out = out; a.o = ospec;
   int splits = sms / ((tiles + 1) / 2 * 2);                                // K is split until the grid fills the SMs
   const int kblocks = K / TK;
   if (splits > kblocks / 8) splits = kblocks / 8;          // at least 8 stages of work per CTA
@@ -312,7 +319,7 @@ static int gemm_4bit_wide(int batch, int N, int K, const T *A, const unsigned ch
     const size_t total = (size_t)batch * N;
     int blocks = (int)((total + 255) / 256);
     if (blocks > sms * 8) blocks = sms * 8;
-    g4::k_gemm4_finalize<T><<<blocks, 256, 0, st>>>(a.ws, bias, out, a.splits, batch, N);
+    g4::k_gemm4_finalize<T><<<blocks, 256, 0, st>>>(a.ws, bias, out, a.splits, batch, N, ospec);
     check_launch("gemm_4bit (finalize)");
     if (ws_from_pool) cudaFreeAsync(a.ws, st);
   }

@@ -192,6 +192,12 @@ BNB_B200_API void cbnb_peer_barrier(unsigned int *counter, const unsigned int *s
  * B packed [N, K/2], out [batch, N] T. tcgen05 kind::f16, TMEM fp32 accumulators. */
 BNB_B200_API int cgemm_4bit_fp16(int batch, int N, int K, void *A, unsigned char *B, float *absmax, float *datatype, void *bias, void *out, int blocksize);
 BNB_B200_API int cgemm_4bit_bf16(int batch, int N, int K, void *A, unsigned char *B, float *absmax, float *datatype, void *bias, void *out, int blocksize);
+/* N-sharded form of the fused GEMM (bnb_b200/parallel.py; SURVEY 8e, BASELINE config 5 at batch > 1): `out` is the base of
+ * this rank's column slice inside the gathered [batch, ldo] buffer, peer_outs[i] the same address in peer i's copy of that
+ * buffer (NVLink peer mappings, <= 7 peers); the epilogue stores the slice into all of them, i.e. it IS the output
+ * all-gather (the reference has no multi-GPU path; parallel.py's fallback is one NCCL all-gather per linear). */
+BNB_B200_API int cgemm_4bit_push_fp16(int batch, int N, int K, void *A, unsigned char *B, float *absmax, float *datatype, void *bias, void *out, int blocksize, long ldo, void **peer_outs, int npeers);
+BNB_B200_API int cgemm_4bit_push_bf16(int batch, int N, int K, void *A, unsigned char *B, float *absmax, float *datatype, void *bias, void *out, int blocksize, long ldo, void **peer_outs, int npeers);
 
 /* B200-native int8 GEMM on ROW-MAJOR operands (the layout tcgen05 + TMA consume directly):
  * C[i,j] = sum_k A[i,k] * B[j,k]; A [m,k], B [n,k] int8 row-major (K-major), C int32 row-major [m,n]. */

@@ -252,3 +252,27 @@ def test_gemm_4bit_cold_caches(F, batch, N, K):
             first = y.clone()
             assert float((y.double() - ref).norm() / ref.norm()) < 4e-3
         assert torch.equal(y.view(torch.int16), first.view(torch.int16)), f"launch {it} differs from launch 0"
+
+
+@pytest.mark.parametrize("batch", [8, 32, 64, 200])
+def test_gemm_4bit_strided_output_and_peer_stores(F, batch):
+    """N-sharded form (cgemm_4bit_push_*): the result goes into a column slice of a wider [batch, ldo] buffer and, through
+    peer_outs, into the same slice of other copies of that buffer.  One GPU stands in for the peers (a second and a third
+    buffer on the same device); everything outside the slice must stay untouched, and the slice must carry the bits of the
+    plain call."""
+    torch.manual_seed(batch)
+    N, K, ldo, off = 384, 2048, 1024, 256
+    W = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
+    x = torch.randn(batch, K, device="cuda").bfloat16()
+    bias = (torch.randn(N, device="cuda") * 0.1).bfloat16()
+    q, st = F.quantize_4bit(W, blocksize=64, compress_statistics=True, quant_type="nf4")
+    plain = F.gemm_4bit(x, q.t(), st, bias=bias, out=torch.empty(batch, N, dtype=torch.bfloat16, device="cuda"))
+    assert plain is not None
+    bufs = [torch.full((batch, ldo), 7.0, dtype=torch.bfloat16, device="cuda") for _ in range(3)]
+    peer_ptrs = [b.data_ptr() + off * b.element_size() for b in bufs[1:]]
+    y = F.gemm_4bit(x, q.t(), st, bias=bias, out=bufs[0][:, off:off + N], peer_outs=peer_ptrs)
+    assert y is not None
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert torch.equal(b[:, off:off + N].contiguous().view(torch.int16), plain.view(torch.int16))
+        assert bool((b[:, :off] == 7.0).all()) and bool((b[:, off + N:] == 7.0).all())
