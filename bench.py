@@ -439,11 +439,14 @@ def run_stack(args, workload, layers, full, world, rank, dev, sampler=None):
                     xv = x_dev[:, offs_k[ids[0]]:offs_k[ids[0] + 1]]
                     if fuse_sharded and len(ids) > 1:
                         sharded_gemv_push_multi(xv, [mats[i][0] for i in ids], [mats[i][1] for i in ids], peers, ids)
+                    elif B > 1:
+                        for i in ids:
+                            sharded_gemm_push(x_dev[:, offs_k[i]:offs_k[i + 1]], mats[i][0], mats[i][1], peers, i)
                     else:
                         for i in ids:
                             sharded_gemv_push(x_dev[:, offs_k[i]:offs_k[i + 1]], mats[i][0], mats[i][1], peers, i)
                     peers.barrier()
-            if peers.offsets[-1] + peers.sizes[-1] == n_total:
+            if B == 1 and peers.offsets[-1] + peers.sizes[-1] == n_total:
                 y_host.copy_(peers.buf[:n_total].view(B, n_total), non_blocking=True)   # gathered vectors, straight from symmetric memory
             else:
                 for j, (_, _, Nj, _) in enumerate(mats):
