@@ -54,9 +54,9 @@ __device__ __forceinline__ float2 lds64f(uint32_t saddr) {
 // CG = 2: a CTA pair (cluster of two) computes 256 weight rows; each CTA dequantises ITS 128 rows into its own TMEM and
 // loads ITS half of the activation rows, the leader issues tcgen05.mma.cta_group::2 (M = 256).  Halves the activation
 // traffic through shared memory, the estimated bound of the one-CTA kernel at NB >= 128.
-template <typename T, int G, int CG>   // G dequant groups of four warps (<= stages)
+template <typename T, int G, int CG, bool PUSH>   // G dequant groups of four warps (<= stages); PUSH: see gemm_4bit_small.cuh
 __global__ void __launch_bounds__(threads_for(G), 1) k_gemm4_wide(const __grid_constant__ CUtensorMap tmX,
-                                                          const __grid_constant__ CUtensorMap tmW, const Args a) {
+                                                          const __grid_constant__ CUtensorMap tmW, const __grid_constant__ Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int kDqWarps = 4 * G;
   const int NB = a.NB;
@@ -243,10 +243,14 @@ __global__ void __launch_bounds__(threads_for(G), 1) k_gemm4_wide(const __grid_c
             const float acc = __uint_as_float(v[j]);
             if (a.splits == 1) {
               const T v = from_float<T>(__fadd_rn(acc, bias));
-              reinterpret_cast<T *>(a.out)[(size_t)b * a.o.ldo + orow] = v;
-#pragma unroll
-              for (int p = 0; p < 7; p++)                                  // NVLink peer stores: the all-gather of an N-sharded stack
-                if (p < a.o.npeers) reinterpret_cast<T *>(a.o.peer[p])[(size_t)b * a.o.ldo + orow] = v;
+              if (PUSH) {
+                reinterpret_cast<T *>(a.out)[(size_t)b * a.o.ldo + orow] = v;
+#pragma unroll 1
+                for (int p = 0; p < a.o.npeers; p++)                       // NVLink peer stores: the all-gather of an N-sharded stack
+                  reinterpret_cast<T *>(a.o.peer[p])[(size_t)b * a.o.ldo + orow] = v;   // (param space, indexed in place: __grid_constant__)
+              } else {
+                reinterpret_cast<T *>(a.out)[(size_t)b * a.N + orow] = v;
+              }
             }
             else a.ws[((size_t)split * a.batch + b) * a.N + orow] = acc;
           }
@@ -295,24 +299,26 @@ static int gemm_4bit_wide(int batch, int N, int K, const T *A, const unsigned ch
   }
   static int g_env = -1;   // BNB_B200_GEMM4_WIDE_G=3: three dequant groups at every width (A/B measurements)
   if (g_env < 0) { const char *e = getenv("BNB_B200_GEMM4_WIDE_G"); g_env = (e && e[0] == '3') ? 3 : 4; }
-  if (pair) {
-    ensure_max_dynamic_smem(reinterpret_cast<const void *>(k_gemm4_wide<T, 4, 2>), kSmemBytes, "gemm_4bit wide smem attr");
+  const bool push = ospec.npeers > 0 || ospec.ldo != N;
+  auto launch = [&](auto kfn, int G, bool cluster) {
+    ensure_max_dynamic_smem(reinterpret_cast<const void *>(kfn), kSmemBytes, "gemm_4bit wide smem attr");
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((tiles + 1) / 2 * 2, a.splits);
-    cfg.blockDim = dim3(threads_for(4));
+    cfg.gridDim = dim3(cluster ? (tiles + 1) / 2 * 2 : tiles, a.splits);
+    cfg.blockDim = dim3(threads_for(G));
     cfg.dynamicSmemBytes = kSmemBytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, k_gemm4_wide<T, 4, 2>, tmX, tmW, a);
+    cfg.attrs = attr; cfg.numAttrs = cluster ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kfn, tmX, tmW, a);
+  };
+  if (pair) {
+    if (push) launch(k_gemm4_wide<T, 4, 2, true>, 4, true); else launch(k_gemm4_wide<T, 4, 2, false>, 4, true);
   } else if (stages_for(a.NB, 1) >= 4 && g_env == 4) {
-    ensure_max_dynamic_smem(reinterpret_cast<const void *>(k_gemm4_wide<T, 4, 1>), kSmemBytes, "gemm_4bit wide smem attr");
-    k_gemm4_wide<T, 4, 1><<<dim3(tiles, a.splits), threads_for(4), kSmemBytes, st>>>(tmX, tmW, a);
+    if (push) launch(k_gemm4_wide<T, 4, 1, true>, 4, false); else launch(k_gemm4_wide<T, 4, 1, false>, 4, false);
   } else {
-    ensure_max_dynamic_smem(reinterpret_cast<const void *>(k_gemm4_wide<T, 3, 1>), kSmemBytes, "gemm_4bit wide smem attr");
-    k_gemm4_wide<T, 3, 1><<<dim3(tiles, a.splits), threads_for(3), kSmemBytes, st>>>(tmX, tmW, a);
+    if (push) launch(k_gemm4_wide<T, 3, 1, true>, 3, false); else launch(k_gemm4_wide<T, 3, 1, false>, 3, false);
   }
   check_launch("gemm_4bit (wide, tcgen05)");
   if (a.splits > 1) {
