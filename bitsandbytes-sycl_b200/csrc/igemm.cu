@@ -102,7 +102,7 @@ struct IgemmArgs {
 
 template <int EPI, int CG>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
-k_igemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmArgs a) {
+k_igemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ IgemmArgs a) {
   constexpr int kStages = stages_for(CG), kStageBytes = stage_bytes(CG);
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
