@@ -564,7 +564,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 template <typename T, bool NESTED, int DEPTH = 2, int WARPS = 16, bool MULTI = false>
-__global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(const GemvArgs a, int x_blocks_padded, int tiles_total) {
+__global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) k_gemv4_bc(const __grid_constant__ GemvArgs a, int x_blocks_padded, int tiles_total) {
   // shared memory: [0, 64 KB) byte LUT (entry stride 256 B, one word per lane) | code2 | x | partial sums.
   // The lookup address is  LUT base (uniform register) + PRMT(byte << 8 | lane * 4): no alignment requirement.
   extern __shared__ __align__(1024) unsigned char smem[];
