@@ -74,24 +74,42 @@ __global__ void __launch_bounds__(256) k_col_row_stats(const __half *__restrict_
       }
     }
   }
-  float cmax[8];
+  // |x| >= 0, and padded / outlier entries count as 0.  Column maxima are kept as packed fp16 pairs (a maximum of halves is
+  // exact in fp16): |x| is a mask, eight columns advance with four HMNMX2, and a chunk goes element by element only when
+  // its own maximum reaches the threshold (compared in fp32 like the reference) -- ~2 instructions per element instead of 6.
+  __half2 cmax2[4];
 #pragma unroll
-  for (int j = 0; j < 8; j++) cmax[j] = 0.0f;  // |x| >= 0, and padded / outlier entries count as 0
+  for (int k = 0; k < 4; k++) cmax2[k] = __float2half2_rn(0.0f);
 #pragma unroll
   for (int h = 0; h < kStatWarpRows / 8; h++) {
     float rm[8];
     int cn[8];
 #pragma unroll
     for (int u = 0; u < 8; u++) {
-      const __half *p = reinterpret_cast<const __half *>(&raw[h * 8 + u]);
+      const uint4 rw = raw[h * 8 + u];
+      const uint32_t aw[4] = {rw.x & 0x7FFF7FFFu, rw.y & 0x7FFF7FFFu, rw.z & 0x7FFF7FFFu, rw.w & 0x7FFF7FFFu};
+      const __half2 *a2 = reinterpret_cast<const __half2 *>(aw);
+      const __half2 m = __hmax2(__hmax2(a2[0], a2[1]), __hmax2(a2[2], a2[3]));
+      const float chunk_max = fmaxf(__low2float(m), __high2float(m));     // NaN ignored by __hmax2 / fmaxf, as below
       float rmax = 0.0f;
       int cnt = 0;
+      if (SPARSE && chunk_max >= thr) {
+        const __half *p = reinterpret_cast<const __half *>(aw);
+        uint32_t kept[4];
+        __half *kp = reinterpret_cast<__half *>(kept);
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        float v = fabsf(__half2float(p[j]));
-        if (SPARSE && v >= thr) { cnt++; v = 0.0f; }
-        cmax[j] = fmaxf(cmax[j], v);
-        rmax = fmaxf(rmax, v);
+        for (int j = 0; j < 8; j++) {
+          float v = __half2float(p[j]);
+          if (v >= thr) { cnt++; v = 0.0f; }
+          kp[j] = __float2half_rn(v);                                     // exact: v is a half or zero
+          rmax = fmaxf(rmax, v);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) cmax2[k] = __hmax2(cmax2[k], *reinterpret_cast<const __half2 *>(&kept[k]));
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) cmax2[k] = __hmax2(cmax2[k], a2[k]);
+        rmax = fmaxf(chunk_max, 0.0f);                                    // a chunk of NaNs only: 0, as the element loop gives
       }
       rm[u] = rmax;
       cn[u] = cnt;
@@ -106,6 +124,9 @@ __global__ void __launch_bounds__(256) k_col_row_stats(const __half *__restrict_
         nnz_count_row[((long)(r / 16) * col_tiles + ct) * 16 + (r % 16) + 1] = (r < rows) ? cn[0] : 0;
     }
   }
+  float cmax[8];
+#pragma unroll
+  for (int k = 0; k < 4; k++) { cmax[2 * k] = __low2float(cmax2[k]); cmax[2 * k + 1] = __high2float(cmax2[k]); }
 #pragma unroll
   for (int j = 0; j < 8; j++) atomicMax(&s_cmax[lane * 8 + j], __float_as_int(cmax[j]));
   __syncthreads();
