@@ -155,6 +155,12 @@ void get_col_row_stats(const __half *A, float *rowStats, float *colStats, int *n
 // out_row = 0 and a COO entry at nnz_row_ptr[tile*16 + r%16] + (rank of the column inside the segment)
 // -- ascending column order inside each (tile,row) segment, so the COO is deterministic.
 // ------------------------------------------------------------------------------------------------
+// == quant_s8 of an already scaled value: rint, saturate to int8, NaN -> 0, in one instruction; the byte sits in bits [0, 8)
+__device__ __forceinline__ uint32_t f2s8_sat(float x) {
+  int q;
+  asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(q) : "f"(x));
+  return (uint32_t)q;
+}
 __device__ __forceinline__ int quant_s8(float x, float scale) {
   int q = __float2int_rn(__fmul_rn(x, scale));  // NaN -> 0, saturates at int32
   return max(-128, min(127, q));
@@ -178,10 +184,11 @@ __global__ void __launch_bounds__(256) k_double_rowcol_quant(const __half *__res
 #pragma unroll
   for (int j = 0; j < 8; j++) cscale[j] = (c0 + j < cols) ? __fdiv_rn(127.0f, colStats[c0 + j]) : 0.0f;
 
-  for (int rb = 0; rb < kBandRows; rb += 4) {
-    uint4 raw[4];
+  constexpr int kRB = 4;                          // rows in flight per warp (8 measured the same 20.7 us)
+  for (int rb = 0; rb < kBandRows; rb += kRB) {
+    uint4 raw[kRB];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < kRB; u++) {
       const int r = r0 + rb + u;
       raw[u] = make_uint4(0, 0, 0, 0);
       if (r < rows) {
@@ -196,22 +203,26 @@ __global__ void __launch_bounds__(256) k_double_rowcol_quant(const __half *__res
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < kRB; u++) {
       const int r = r0 + rb + u;
       if (r >= rows) continue;  // warp-uniform
       const __half *p = reinterpret_cast<const __half *>(&raw[u]);
       const float rscale = __fdiv_rn(127.0f, __ldg(rowStats + r));
-      uint32_t qr[2] = {0, 0}, qc[2] = {0, 0};
+      uint32_t qr[2], qc[2];
       uint32_t outlier_mask = 0;
+      uint32_t br[8], bc[8];                      // rint + saturate in one conversion each, bytes gathered with three PRMT per word
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         const float x = __half2float(p[j]);
-        int r8;
-        if (sparse && fabsf(x) >= thr && c0 + j < cols) { r8 = 0; outlier_mask |= 1u << j; }
-        else r8 = quant_s8(x, rscale);
-        const int c8 = quant_s8(x, cscale[j]);
-        qr[j >> 2] |= (uint32_t)(r8 & 0xFF) << (8 * (j & 3));
-        qc[j >> 2] |= (uint32_t)(c8 & 0xFF) << (8 * (j & 3));
+        const bool outl = sparse && fabsf(x) >= thr && c0 + j < cols;
+        if (outl) outlier_mask |= 1u << j;
+        br[j] = outl ? 0u : f2s8_sat(__fmul_rn(x, rscale));
+        bc[j] = f2s8_sat(__fmul_rn(x, cscale[j]));
+      }
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        qr[h] = __byte_perm(__byte_perm(br[4 * h], br[4 * h + 1], 0x0040), __byte_perm(br[4 * h + 2], br[4 * h + 3], 0x0040), 0x5410);
+        qc[h] = __byte_perm(__byte_perm(bc[4 * h], bc[4 * h + 1], 0x0040), __byte_perm(bc[4 * h + 2], bc[4 * h + 3], 0x0040), 0x5410);
       }
       const long o = (long)r * cols + c0;
       if (VEC) {
