@@ -12,7 +12,7 @@
 
 namespace bnb {
 
-constexpr int kBandRows = 32;   // rows per warp band (2 of the reference's 16-row nnz tiles)
+constexpr int kBandRows = 32;   // rows per warp band (2 of the reference's 16-row nnz tiles; 16 measured the same 20.7 us)
 constexpr float kMMDequantConst = 6.200012e-05f;  // kernel_quant.cpp:3846
 
 __device__ __forceinline__ void atomic_max_nonneg(float *addr, float v) {
