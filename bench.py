@@ -41,8 +41,8 @@ for p in (ROOT, PKG_DIR):
 
 # DRAM bytes per algorithmic byte of the GEMV kernel: a CONSTANT taken from the committed ncu --set full capture of the
 # named round (dram__bytes_read.sum + dram__bytes_write.sum of one 11008x4096 launch), not measured inside this run
-NCU_TRAFFIC_RATIO = 23.306496 / 23.291200
-NCU_TRAFFIC_SOURCE = "ncu-derived constant, round 1: dram bytes / algorithmic bytes = 1.0007 (profiles/r1_ncu_summaries.txt)"
+NCU_TRAFFIC_RATIO = 6704385024.0 / (2 * 3346012160.0)
+NCU_TRAFFIC_SOURCE = "ncu-derived constant, round 2: dram__bytes_read + write over the 448 GEMV launches of two bench steps / algorithmic bytes = 1.0018 (profiles/r2_gemv_dram_traffic.txt)"
 GEMV_KERNEL_NAME = "k_gemv4_bc<bf16,nested>"
 LAYER_SHAPES_7B = [(4096, 4096)] * 4 + [(11008, 4096)] * 2 + [(4096, 11008)]
 LAYER_SHAPES_70B = [(8192, 8192), (1024, 8192), (1024, 8192), (8192, 8192), (28672, 8192), (28672, 8192), (8192, 28672)]
