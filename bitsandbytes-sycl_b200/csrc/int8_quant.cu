@@ -41,20 +41,23 @@ __device__ __forceinline__ void warp_reduce_scatter8(V (&v)[8], int lane, Op op)
   v[0] = op(v[0], __shfl_xor_sync(0xffffffffu, v[0], 16));
 }
 
-constexpr int kStatWarpRows = 16;   // rows per warp: one of the reference's 16-row nnz tiles, all 16 loads in flight at once
+constexpr int kStatWarpRows = 8;    // rows per warp, all loads in flight at once (16 rows = 64 registers held the SM at 30 % of its warps)
 constexpr int kStatCtaRows = 8 * kStatWarpRows;
 
 // CTA = 8 warps stacked on ONE 256-column segment (128 rows): column maxima meet in shared memory first, so the global
 // atomics are 256 per CTA; row maxima: one atomic per (row, segment), issued by 8 lanes at a time.
+// Persistent: four CTAs per SM walk the (row band, column tile) units, so the whole matrix is requested in one wave of
+// resident CTAs instead of 3.5 one-shot CTAs per SM with a ragged tail.
 template <bool VEC, bool SPARSE>
-__global__ void __launch_bounds__(256) k_col_row_stats(const __half *__restrict__ A, float *rowStats, float *colStats,
-                                                       int *nnz_count_row, float thr, int rows, int cols, int col_tiles) {
+__global__ void __launch_bounds__(256, 4) k_col_row_stats(const __half *__restrict__ A, float *rowStats, float *colStats,
+                                                          int *nnz_count_row, float thr, int rows, int cols, int col_tiles, int units) {
   __shared__ int s_cmax[256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ct = blockIdx.x % col_tiles, rband = blockIdx.x / col_tiles;
+  const int rows16 = ((rows + 15) / 16) * 16;
+  for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+  const int ct = unit % col_tiles, rband = unit / col_tiles;
   const int c0 = ct * 256 + lane * 8;
   const int r0 = rband * kStatCtaRows + warp * kStatWarpRows;
-  const int rows16 = ((rows + 15) / 16) * 16;
   s_cmax[threadIdx.x] = 0;
   __syncthreads();
 
@@ -132,6 +135,8 @@ __global__ void __launch_bounds__(256) k_col_row_stats(const __half *__restrict_
   __syncthreads();
   const int c = ct * 256 + threadIdx.x;
   if (c < cols) atomicMax(reinterpret_cast<int *>(colStats + c), s_cmax[threadIdx.x]);
+  __syncthreads();                                   // s_cmax is reset by the next unit
+  }
 }
 
 void get_col_row_stats(const __half *A, float *rowStats, float *colStats, int *nnz_count_row, float thr, int rows,
@@ -139,10 +144,15 @@ void get_col_row_stats(const __half *A, float *rowStats, float *colStats, int *n
   if (rows <= 0 || cols <= 0) return;
   const int col_tiles = ceil_div(cols, 256);
   const int rbands = ceil_div(ceil_div(rows, 16) * 16, kStatCtaRows);
-  const unsigned grid = (unsigned)((long)rbands * col_tiles);
+  const long units_l = (long)rbands * col_tiles;
+  if (units_l > 0x7fffffffL) { latch_error(cudaErrorInvalidValue, "get_col_row_stats: matrix too large"); return; }
+  const int units = (int)units_l;
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const unsigned grid = (unsigned)(units < sms * 4 ? units : sms * 4);
   const bool vec = (cols % 8 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0);
   cudaStream_t st = current_stream();
-#define STATS_LAUNCH(V_, S_) k_col_row_stats<V_, S_><<<grid, 256, 0, st>>>(A, rowStats, colStats, nnz_count_row, thr, rows, cols, col_tiles)
+#define STATS_LAUNCH(V_, S_) k_col_row_stats<V_, S_><<<grid, 256, 0, st>>>(A, rowStats, colStats, nnz_count_row, thr, rows, cols, col_tiles, units)
   if (thr > 0.0f) { if (vec) STATS_LAUNCH(true, true); else STATS_LAUNCH(false, true); }
   else { if (vec) STATS_LAUNCH(true, false); else STATS_LAUNCH(false, false); }
 #undef STATS_LAUNCH
