@@ -193,6 +193,10 @@ __global__ void __launch_bounds__(256) k_double_rowcol_quant(const __half *__res
   float cscale[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) cscale[j] = (c0 + j < cols) ? __fdiv_rn(127.0f, colStats[c0 + j]) : 0.0f;
+  // the band's 32 row scales: one load + one IEEE divide per lane up front, broadcast by shuffle in the loop (a load and a
+  // divide per row inside the loop put an L2 round trip in front of every four rows)
+  static_assert(kBandRows == 32, "one row scale per lane");
+  const float my_rscale = (r0 + lane < rows) ? __fdiv_rn(127.0f, __ldg(rowStats + r0 + lane)) : 0.0f;
 
   constexpr int kRB = 4;                          // rows in flight per warp (8 measured the same 20.7 us)
   for (int rb = 0; rb < kBandRows; rb += kRB) {
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(256) k_double_rowcol_quant(const __half *__res
       const int r = r0 + rb + u;
       if (r >= rows) continue;  // warp-uniform
       const __half *p = reinterpret_cast<const __half *>(&raw[u]);
-      const float rscale = __fdiv_rn(127.0f, __ldg(rowStats + r));
+      const float rscale = __shfl_sync(0xffffffffu, my_rscale, rb + u);
       uint32_t qr[2], qc[2];
       uint32_t outlier_mask = 0;
       uint32_t br[8], bc[8];                      // rint + saturate in one conversion each, bytes gathered with three PRMT per word
